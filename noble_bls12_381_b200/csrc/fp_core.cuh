@@ -1,0 +1,88 @@
+// Fp core for BLS12-381 on sm_100a: 12 x 32-bit limbs, Montgomery form (R = 2^384).
+//
+// Replaces the reference's `Fp` bigint arithmetic (math.ts:215-291: every op is a heap bigint `*`
+// followed by `%`, math.ts:80-83) with register-resident carry chains:
+//   * acc_mac   : 768-bit accumulator += a*b       (144 IMAD.WIDE.U32[.X], no reduction)
+//   * acc_redc  : Montgomery reduction of the accumulator (12 x (1 IMAD + 12 IMAD.WIDE.U32.X))
+//   * add12/sub12/csub: carry-chain add/sub and conditional subtraction of k*p
+// "Lazy reduction": tower formulas accumulate many products into one accumulator and reduce once.
+//
+// The generated primitives also have a portable C++ body (`#else` of __CUDA_ARCH__) used ONLY by the CPU
+// emulation tests (tests/emu) to validate interpreter + program logic without a GPU.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FPC_DEV __host__ __device__ __forceinline__
+#define FPC_CONST static __device__ __constant__ const
+#else
+#define FPC_DEV static inline
+#define FPC_CONST static const
+#endif
+
+#include "fp_core_gen.cuh"
+
+namespace fpc {
+
+FPC_DEV void acc_zero(Acc& A) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) A.e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 22; ++i) A.o[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) A.c[i] = 0;
+}
+
+FPC_DEV void copy12(uint32_t* r, const uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[i] = a[i];
+}
+
+FPC_DEV void zero12(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[i] = 0;
+}
+
+// r = (r >= kp) ? r - kp : r      (kp = table of k*p)
+FPC_DEV void csub(uint32_t* r, const uint32_t* kp) {
+    uint32_t t[12];
+    uint32_t borrow = sub12(t, r, kp);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[i] = borrow ? r[i] : t[i];
+}
+
+// bring a value < 2^rounds * p (rounds <= 3) into [0, p)
+FPC_DEV void correct(uint32_t* r, int rounds) {
+    if (rounds >= 3) csub(r, kP4);
+    if (rounds >= 2) csub(r, kP2);
+    if (rounds >= 1) csub(r, kP1);
+}
+
+// r = p - a   (a in [0,p] -> r in [0,p]; NOT canonical for a == 0, fine as a multiplicand)
+FPC_DEV void neg_raw(uint32_t* r, const uint32_t* a) { (void)sub12(r, kP1, a); }
+
+// Montgomery product, canonical output: r = a*b/R mod p  (a, b < p)
+FPC_DEV void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    Acc A;
+    acc_zero(A);
+    acc_mac(A, a, b);
+    acc_redc(A, r);
+    csub(r, kP1);
+}
+
+// r = a + b mod p, a, b canonical
+FPC_DEV void add_mod(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    (void)add12(r, a, b);
+    csub(r, kP1);
+}
+
+// r = a - b mod p, a, b canonical
+FPC_DEV void sub_mod(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t t[12];
+    uint32_t borrow = sub12(r, a, b);
+    (void)add12(t, r, kP1);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[i] = borrow ? t[i] : r[i];
+}
+
+}  // namespace fpc

@@ -1,0 +1,228 @@
+// Tower-VM: the B200 execution model for the wide (Fp12) part of the pairing hot path.
+//
+// One CTA = VM_WARPS warps x 32 lanes processes 32 pairings at once: LANE = PAIRING.  Every field
+// element of the batch lives in shared memory as a "slot": 12 limbs x 32 lanes, laid out
+// [slot][q=0..2][lane][4 limbs] so that a warp reads a slot with three conflict-free LDS.128.  A warp
+// executes one "micro-op" at a time for all 32 pairings in lock-step (warp-uniform control flow, no
+// divergence, 100% lane use):
+//
+//     dst = MontRed( sum_t X_t * Y_t ) + sum_e Z_e          (mod p, canonical)
+//
+// where each operand is a small signed combination cA*A + cB*B of slots (or a constant) formed in
+// registers while loading.  This single op expresses everything the reference's tower does
+// (math.ts:403-885: Fp2/Fp6/Fp12 multiply, square, sparse multiply, Frobenius, cyclotomic square, line
+// evaluation math.ts:1331-1388) with LAZY REDUCTION: one Montgomery reduction per output coefficient
+// instead of one per Fp product.  The per-warp instruction streams ("programs") are produced by the
+// host-side builder (noble_bls12_381_b200/vmprog) which also schedules independent micro-ops across
+// the warps of a CTA and allocates slots; barriers (`bar.sync`) separate dependent steps.
+//
+// This header is shared by the CUDA kernel (vm_kernel.cu) and the CPU emulation used by the tests
+// (tests/emu/vm_emu.cpp) -- the emulation exists to validate programs without a GPU and is not part
+// of the shipped library.
+#pragma once
+#include <cstdint>
+#include "fp_core.cuh"
+
+namespace vm {
+
+static constexpr int kRecWords = 32;       // one micro-op record = 128 bytes
+static constexpr int kMaxTerms = 12;
+static constexpr int kMaxEpi = 2;
+static constexpr int kSlotWords = 12 * 32; // 1536 B per slot
+static constexpr int kMaxBuffers = 8;
+static constexpr int kConstSlots = 64;
+
+// ---- record layout -------------------------------------------------------------------------------
+// word 0 (header): [7:0] opcode  [15:8] dst  [19:16] T  [21:20] E  [24:22] ncorr  [25] bar_before
+//                  [26] dst_global  [27] dst_raw (global scratch, no byte swap)  [31:28] reserved
+// word 1 (aux)   : [7:0] dst buffer id  [15:8] dst field   [23:16] lane xor mask (for XLANE terms)
+// words 2..25    : T terms, 2 words each:
+//     word A: [7:0] xA  [15:8] xB  [19:16] cA (signed 4-bit)  [23:20] cB  [31:24] xflags
+//     word B: [7:0] yA  [15:8] yB  [19:16] cA                [23:20] cB  [31:24] yflags
+// words 26..29   : E epilogue operands, same 1-word operand encoding in words 26 and 28 (27/29 spare)
+// operand flags  : bit0 CONST  (A/B index the constant table instead of slots)
+//                  bit1 GLOBAL (A = buffer id, B = field index: wire-format big-endian 48-byte field)
+//                  bit2 XLANE  (read the slot column of lane ^ mask)
+enum : uint32_t { OP_NOP = 0, OP_MAC = 1 };
+enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4 };
+static constexpr uint32_t H_BAR = 1u << 25;
+static constexpr uint32_t H_DSTG = 1u << 26;
+static constexpr uint32_t H_DSTRAW = 1u << 27;
+
+struct Buffer {
+    uint8_t* base;      // device pointer
+    uint32_t stride;    // bytes per item
+    uint32_t pad;
+};
+
+struct Launch {
+    const uint32_t* prog;   // [warps][nrec][32]
+    const uint32_t* consts; // [nconst][12] Montgomery-form (or plain) constants
+    uint32_t nrec;
+    uint32_t nconst;
+    uint32_t nslots;        // shared-memory slots
+    uint32_t nfar;          // far slots (global scratch) per CTA
+    uint32_t n_items;
+    uint32_t pad;
+    uint32_t* far;          // [ctas][nfar][kSlotWords]
+    Buffer buf[kMaxBuffers];
+};
+
+// ---- per-lane execution context -------------------------------------------------------------------
+struct Ctx {
+    uint32_t* slots;         // shared memory slots
+    const uint32_t* consts;  // constant table (shared memory copy on device)
+    uint32_t* far;           // this CTA's far slots
+    uint32_t nslots;
+    uint32_t lane;
+    uint32_t item;           // global item index of this lane (clamped to n_items-1 for loads)
+    bool store_ok;           // lane < n_items
+    const Buffer* buf;
+};
+
+FPC_DEV uint32_t bswap32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return __builtin_bswap32(v);
+#endif
+}
+
+FPC_DEV void load_slot(uint32_t* r, const Ctx& c, uint32_t slot, uint32_t lane) {
+    if (slot < c.nslots) {
+        const uint32_t* s = c.slots + slot * kSlotWords + lane * 4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
+            r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+#else
+        for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
+#endif
+    } else {
+        const uint32_t* s = c.far + (slot - c.nslots) * kSlotWords + lane * 4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
+            r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+#else
+        for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
+#endif
+    }
+}
+
+FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
+    uint32_t* s = (slot < c.nslots) ? c.slots + slot * kSlotWords + c.lane * 4
+                                    : c.far + (slot - c.nslots) * kSlotWords + c.lane * 4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        *reinterpret_cast<uint4*>(s + q * 128) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+#else
+    for (int q = 0; q < 3; ++q)
+        for (int k = 0; k < 4; ++k) s[q * 128 + k] = r[4 * q + k];
+#endif
+}
+
+// wire format: 48-byte big-endian field element -> 12 little-endian limbs
+FPC_DEV void load_wire(uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field) {
+    const Buffer& b = c.buf[bufid];
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(b.base + (size_t)c.item * b.stride + field * 48u);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r[k] = bswap32(p[11 - k]);
+}
+
+FPC_DEV void store_wire(const uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field) {
+    if (!c.store_ok) return;
+    const Buffer& b = c.buf[bufid];
+    uint32_t* p = reinterpret_cast<uint32_t*>(b.base + (size_t)c.item * b.stride + field * 48u);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) p[11 - k] = bswap32(r[k]);
+}
+
+FPC_DEV int sext4(uint32_t v) { return (int)((v & 0xF) ^ 8) - 8; }
+
+// v = k * v for k in 1..4 (no reduction; caller guarantees k*v < 2^384)
+FPC_DEV void scale_raw(uint32_t* v, int k) {
+    if (k == 1) return;
+    uint32_t t[12];
+    fpc::copy12(t, v);
+    (void)fpc::add12(v, v, v);                 // 2v
+    if (k == 3) (void)fpc::add12(v, v, t);     // 3v
+    if (k == 4) (void)fpc::add12(v, v, v);     // 4v
+}
+
+FPC_DEV void load_one(uint32_t* r, const Ctx& c, uint32_t idx, uint32_t flags, uint32_t xmask) {
+    if (flags & F_CONST) {
+        const uint32_t* s = c.consts + idx * 12;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = s[k];
+    } else {
+        load_slot(r, c, idx, (flags & F_XLANE) ? (c.lane ^ xmask) : c.lane);
+    }
+}
+
+// operand = cA*A + cB*B  (negative coefficients via p - X), unreduced
+FPC_DEV void load_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask) {
+    const uint32_t a = w & 0xFF, b = (w >> 8) & 0xFF, flags = w >> 24;
+    const int ca = sext4(w >> 16), cb = sext4(w >> 20);
+    if (flags & F_GLOBAL) {
+        load_wire(r, c, a, b);
+        return;
+    }
+    load_one(r, c, a, flags, xmask);
+    if (ca < 0) fpc::neg_raw(r, r);
+    scale_raw(r, ca < 0 ? -ca : ca);
+    if (cb != 0) {
+        uint32_t u[12];
+        load_one(u, c, b, flags, xmask);
+        if (cb < 0) fpc::neg_raw(u, u);
+        scale_raw(u, cb < 0 ? -cb : cb);
+        (void)fpc::add12(r, r, u);
+    }
+}
+
+// Executes one record for one lane.  `W(i)` returns record word i (warp shuffle on device).
+template <class WordFn>
+FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
+    const uint32_t op = hdr & 0xFF;
+    if (op == OP_NOP) return;
+    const uint32_t dst = (hdr >> 8) & 0xFF;
+    const uint32_t T = (hdr >> 16) & 0xF;
+    const uint32_t E = (hdr >> 20) & 0x3;
+    const int ncorr = (int)((hdr >> 22) & 0x7);
+    const uint32_t xmask = (aux >> 16) & 0xFF;
+
+    uint32_t r[12];
+    if (T > 0) {
+        fpc::Acc A;
+        fpc::acc_zero(A);
+        for (uint32_t t = 0; t < T; ++t) {
+            uint32_t x[12], y[12];
+            load_operand(x, c, W(2 + 2 * t), xmask);
+            load_operand(y, c, W(3 + 2 * t), xmask);
+            fpc::acc_mac(A, x, y);
+        }
+        fpc::acc_redc(A, r);
+    } else {
+        fpc::zero12(r);
+    }
+    for (uint32_t e = 0; e < E; ++e) {
+        uint32_t z[12];
+        load_operand(z, c, W(26 + 2 * e), xmask);
+        (void)fpc::add12(r, r, z);
+    }
+    fpc::correct(r, ncorr);
+    if (hdr & H_DSTG) {
+        store_wire(r, c, aux & 0xFF, (aux >> 8) & 0xFF);
+    } else {
+        store_slot(r, c, dst);
+    }
+}
+
+}  // namespace vm

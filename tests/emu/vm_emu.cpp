@@ -1,0 +1,74 @@
+// CPU emulation of the tower-VM interpreter (noble_bls12_381_b200/csrc/vm.cuh) -- TEST INFRASTRUCTURE.
+// Compiles the *same* exec_record()/fp_core source with g++ (portable bodies of the carry chains) so
+// that programs produced by the builder, and the interpreter logic itself, can be validated on a box
+// without a GPU.  Never linked into the shipped library.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../noble_bls12_381_b200/csrc/vm.cuh"
+
+extern "C" {
+
+// r = a*b/R mod p
+void emu_mont_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::mont_mul(r, a, b); }
+
+// r = (sum a_i*b_i)/R, unreduced, then `rounds` correction rounds
+void emu_mac_redc(int n, const uint32_t* a, const uint32_t* b, int rounds, uint32_t* r) {
+    fpc::Acc A;
+    fpc::acc_zero(A);
+    for (int i = 0; i < n; ++i) fpc::acc_mac(A, a + 12 * i, b + 12 * i);
+    fpc::acc_redc(A, r);
+    fpc::correct(r, rounds);
+}
+
+void emu_add_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::add_mod(r, a, b); }
+void emu_sub_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::sub_mod(r, a, b); }
+
+// Runs a program on n_items items.  bufs: base pointers (host memory), strides in bytes.
+int vm_emu_run(const uint32_t* prog, int warps, int nrec, const uint32_t* consts, int nconst, int nslots,
+               int nfar, int n_items, uint8_t** bases, const uint32_t* strides, int nbuf) {
+    vm::Buffer buf[vm::kMaxBuffers];
+    memset(buf, 0, sizeof(buf));
+    for (int i = 0; i < nbuf && i < vm::kMaxBuffers; ++i) { buf[i].base = bases[i]; buf[i].stride = strides[i]; }
+    std::vector<uint32_t> slots((size_t)nslots * vm::kSlotWords), far((size_t)(nfar ? nfar : 1) * vm::kSlotWords);
+    int nbatch = (n_items + 31) / 32;
+    for (int batch = 0; batch < nbatch; ++batch) {
+        std::vector<int> pc(warps, 0);
+        std::vector<bool> passed(warps, false);  // barrier of record pc[w] already passed
+        for (;;) {
+            bool progress = false, all_done = true;
+            for (int w = 0; w < warps; ++w) {
+                while (pc[w] < nrec) {
+                    const uint32_t* rec = prog + ((size_t)w * nrec + pc[w]) * vm::kRecWords;
+                    if ((rec[0] & vm::H_BAR) && !passed[w]) break;  // wait at barrier
+                    for (uint32_t lane = 0; lane < 32; ++lane) {
+                        vm::Ctx c;
+                        c.slots = slots.data(); c.consts = consts; c.far = far.data(); c.nslots = nslots;
+                        c.lane = lane;
+                        uint32_t item = batch * 32 + lane;
+                        c.store_ok = item < (uint32_t)n_items;
+                        c.item = c.store_ok ? item : (uint32_t)n_items - 1;
+                        c.buf = buf;
+                        vm::exec_record(c, rec[0], rec[1], [&](uint32_t i) { return rec[i]; });
+                    }
+                    passed[w] = false;
+                    ++pc[w];
+                    progress = true;
+                }
+                if (pc[w] < nrec) all_done = false;
+            }
+            if (all_done) break;
+            // every unfinished warp now waits at a barrier: release them together
+            bool all_at_bar = true;
+            for (int w = 0; w < warps; ++w)
+                if (pc[w] >= nrec) { all_at_bar = false; }  // a finished warp can't arrive: program bug
+            if (!all_at_bar) { fprintf(stderr, "vm_emu: barrier count mismatch between warps\n"); return -2; }
+            for (int w = 0; w < warps; ++w) passed[w] = true;
+            (void)progress;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"
