@@ -1,0 +1,251 @@
+#!/usr/bin/env python3
+"""bench.py -- pairings/sec of the B200 engine on BASELINE.json's config 2 (65 536 independent pairings).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n ITEMS] [--impl reference]
+
+One "step" = one pass of the hot path (Miller loop + final exponentiation) over one batch of N_ITEMS
+synthetic pairings (i*G1, i*G2) -- the reference's kilic fixtures are the first 1000 items and are
+byte-compared.  `value` = whole-job pairings/s with inputs resident in HBM (CUDA events on the launching
+stream, max over ranks); `e2e` = the same through the C-ABI host entry point with host buffers
+(H2D + kernel + D2H inside the timed region).  Multi-GPU: independent pairings shard by index, no
+collective on the data path ("weak" scaling: every rank processes N_ITEMS).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP_MUL_PER_PAIRING = 15.4e3  # 14 960 Fp-mul + 1 inversion
+IMAD_PER_FP_MUL = 288  # 12x12 product + 12x12 Montgomery reduction, 32x32->64 multiply-adds
+IMAD_PER_PAIRING = FP_MUL_PER_PAIRING * IMAD_PER_FP_MUL  # ~4.44 M
+BYTES_PER_PAIRING = 288 + 576  # algorithmic HBM bytes
+
+
+def _clock_sampler(stop, samples):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", os.environ.get("LOCAL_RANK", "0"), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+            samples.append([x.strip() for x in out.split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(int(float(s[0])) for s in samples if s[0].replace(".", "").isdigit())
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in samples:
+        for k, nm in enumerate(names):
+            if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                reasons.add(nm)
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(samples[0][1])) if samples[0][1] else None,
+            "reasons": sorted(reasons), "samples": len(samples)}
+
+
+def _oracle_worker(args):
+    """CPU baseline worker: the oracle's pairing (line precompute + Miller + final exp) on `count` items."""
+    start, count = args
+    from oracle import noble_oracle as O
+    p = O.pt_multiply_unsafe(O.G1, O.G1_BASE, start + 1)
+    q = O.pt_multiply_unsafe(O.G2, O.G2_BASE, start + 1)
+    t = time.perf_counter()
+    for _ in range(count):
+        pa, qa = O.pt_to_affine(O.G1, p), O.pt_to_affine(O.G2, q)
+        O.fp12_final_exponentiate(O.miller_loop(O.calc_pairing_precomputes(*qa), pa))
+        p = O.pt_add(O.G1, p, O.G1_BASE)
+        q = O.pt_add(O.G2, q, O.G2_BASE)
+    return count, time.perf_counter() - t
+
+
+def cpu_baseline(per_core: int):
+    """Oracle (Python port of the reference algorithm) on all host cores; returns (pairings/s, cores, n)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    cores = min(cores, 64)
+    t = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_oracle_worker, [(1000 * i, per_core) for i in range(cores)])
+    wall = time.perf_counter() - t
+    n = sum(r[0] for r in res)
+    return n / wall, cores, n
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; node/tsc are absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_core = 6
+    for _ in range(args.warmup and 1):
+        cpu_baseline(1)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, cores, n = cpu_baseline(per_core)
+        vals.append(v)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "pairings/sec", "value": v, "unit": "pairings/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "config 2: independent pairings e(i*G1, i*G2), Miller loop + final exponentiation",
+                   "items_per_step": n},
+        "cpu_baseline": {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_core} pairings per core per step, Python-int restatement of math.ts/index.ts (node/tsc absent on this image)"},
+        "e2e": {"value": v, "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=65536, help="pairings per step per GPU")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import noble_bls12_381_b200 as bls
+    from noble_bls12_381_b200 import synth
+    eng = bls.Engine(local_rank)
+    n = args.n
+    # synthetic inputs: (i*G1, i*G2); every rank processes its own n items (weak scaling, sharded by index)
+    t_gen = time.time()
+    g1, g2 = synth.multiples_wire(n)
+    t_gen = time.time() - t_gen
+    h1 = torch.frombuffer(bytearray(g1), dtype=torch.uint8).pin_memory()
+    h2 = torch.frombuffer(bytearray(g2), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(576 * n, dtype=torch.uint8).pin_memory()
+    d1, d2 = h1.cuda(), h2.cuda()
+    dout = torch.zeros(576 * n, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        eng.pairing_batch_dev(d1.data_ptr(), d2.data_ptr(), n, True, dout.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    # parity inside the bench: the first 1000 outputs are the reference's kilic fixtures
+    gold_path = os.path.join(ROOT, "tests", "golden", "pairing_kilic_1000.bin")
+    parity = None
+    if os.path.exists(gold_path):
+        k = min(n, 1000)
+        parity = bytes(dout[: 576 * k].cpu().numpy().tobytes()) == open(gold_path, "rb").read()[: 576 * k]
+
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
+    th.start()
+    launches0 = eng.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step_resident()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = eng.launch_count() - launches0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+
+    # end-to-end through the C-ABI host entry point (host buffers in, host buffers out)
+    import ctypes
+    e2e_steps = max(1, min(args.steps, 3))
+    out_buf = ctypes.create_string_buffer(576 * n)
+    eng.lib.bls381_pairing_batch(h1.data_ptr(), h2.data_ptr(), n, 1, hout.data_ptr(), None)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = eng.lib.bls381_pairing_batch(h1.data_ptr(), h2.data_ptr(), n, 1, hout.data_ptr(), None)
+        assert rc == 0
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    stop.set()
+    th.join(timeout=2)
+    if parity:
+        k = min(n, 1000)
+        parity = bytes(hout[: 576 * k].numpy().tobytes()) == open(gold_path, "rb").read()[: 576 * k]
+
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    e2e_value = world * n / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        imad_peak = eng.imad_peak()
+        per_gpu = n / (ms_per_step * 1e-3)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "pairings/sec", "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "config 2: %d independent pairings e(i*G1, i*G2) per GPU, Miller loop + final exponentiation, bit-exact vs kilic fixtures" % n,
+                       "items_per_step_per_gpu": n, "parallelism": "shard-by-index x%d, no collective" % world,
+                       "cache": "inputs+outputs+VM scratch (%.0f MB) are re-streamed every step; compute-bound kernel (0.9 KB/pairing), no L2 flush needed" % ((288 + 576) * n / 1e6)},
+            "parity_first_1000_vs_reference_fixtures": parity,
+            "kernel_ms_per_step": kernel_ms,
+            "roofline": {
+                "bound": "imad", "achieved": per_gpu * IMAD_PER_PAIRING / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+                "frac": per_gpu * IMAD_PER_PAIRING / imad_peak,
+                "traffic": None,
+                "note": "integer-multiply pipe bound (SURVEY 8d): achieved = pairings/s/GPU x 15.4k Fp-mul x 288 IMAD; peak = IMAD.WIDE.U32 issue rate measured live on this GPU (bls381_imad_peak)",
+                "hbm": {"achieved": per_gpu * BYTES_PER_PAIRING / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": per_gpu * BYTES_PER_PAIRING / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            },
+            "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": 288 * n, "d2h_bytes_per_step": 576 * n},
+            "gpu_launches": int(launches),
+            "clocks": _clocks_summary(samples),
+            "input_generation_s": t_gen,
+        }
+        if not args.no_cpu_baseline:
+            v, cores, cnt = cpu_baseline(4)
+            line["cpu_baseline"] = {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cnt} pairings (4 per core), Python-int restatement of math.ts/index.ts; reference comment index.ts:719 implies ~43/s/core on V8"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

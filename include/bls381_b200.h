@@ -1,0 +1,101 @@
+/* bls381_b200.h -- C ABI of the B200-native batched BLS12-381 pairing engine.
+ *
+ * Drop-in boundary for the pairing / verify / verifyBatch / aggregate* / sign path of
+ * paulmillr/noble-bls12-381 v1.4.0.  The reference has no FFI of its own (pure TypeScript,
+ * SURVEY.md section 8b): each entry point below states which reference function it replaces
+ * (file:line relative to the reference tree) and INTEGRATION.md shows the N-API / TypeScript and
+ * ctypes bindings a maintainer adds on top.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Host entry points take HOST pointers and copy to/from the
+ *     device internally; `_dev` entry points take DEVICE pointers (inputs already resident in HBM)
+ *     and run on the caller's CUDA stream.
+ *   - Wire format = the reference's own: every field element is 48 bytes big-endian
+ *     (Fp.toBytes, math.ts:288-290).
+ *       G1 affine   : 96 B  = x || y                                     (index.ts:377-378)
+ *       G2 affine   : 192 B = x.c0 || x.c1 || y.c0 || y.c1   (Fp2.toBytes order, math.ts:547-549)
+ *       Fp12        : 576 B = 12 coefficients in the flat order of Fp12.fromBigTwelve /
+ *                     Fp12.toBytes (math.ts:709-714, 882-884)
+ *   - All functions return 0 on success, a negative BLS381_E* code on call-level failure
+ *     (bad argument, CUDA error, library not initialised); bls381_last_error() has the text.
+ *     Per-item conditions are reported through `status[i]` (BLS381_ST_*), so that the wrapper can
+ *     re-create the reference's throw-vs-false behaviour (index.ts:716, :385-386, :635-636, :802-820).
+ *   - The library never keeps caller pointers after a call returns.  Thread-safe per call.
+ *   - There is NO CPU fallback: every entry point fails with BLS381_ENODEV without a CUDA device.
+ */
+#ifndef BLS381_B200_H
+#define BLS381_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLS381_OK 0
+#define BLS381_EINVAL (-1)   /* bad argument */
+#define BLS381_ENODEV (-2)   /* no CUDA device / driver */
+#define BLS381_ECUDA (-3)    /* CUDA runtime error */
+#define BLS381_ENOINIT (-4)  /* bls381_init() not called or failed */
+#define BLS381_EPROGRAM (-5) /* tower-VM program file missing or malformed */
+
+/* per-item status codes */
+#define BLS381_ST_OK 0
+#define BLS381_ST_INFINITY 1        /* 'No pairings at point of Infinity'           index.ts:716 */
+#define BLS381_ST_NOT_ON_CURVE 2    /* 'Invalid G1/G2 point: not on curve'          index.ts:385,635 */
+#define BLS381_ST_NOT_IN_SUBGROUP 3 /* '... must be of prime-order subgroup'        index.ts:386,636 */
+#define BLS381_ST_BAD_ENCODING 4    /* 'Invalid compressed G1 point', bad flags     index.ts:312 */
+#define BLS381_ST_NO_SQRT 5         /* 'Failed to find a square root'               index.ts:518 */
+
+/* Library lifetime.  `device` = CUDA ordinal.  `program_dir` = directory holding the tower-VM program
+ * files (*.b2vm) produced at build time; NULL = "<dir of this shared object>/programs". */
+int bls381_init(int device, const char* program_dir);
+int bls381_shutdown(void);
+const char* bls381_last_error(void);
+/* number of streaming multiprocessors of the initialised device (0 if not initialised) */
+int bls381_sm_count(void);
+
+/* pairing(P, Q, withFinalExponent)                               replaces index.ts:715-722
+ * (the Miller loop math.ts:1331-1388 with fused line evaluation + finalExponentiate math.ts:856-874)
+ * n independent pairings e(P_i, Q_i) of affine, valid, non-infinity points.
+ *   g1  : n x 96 B,  g2 : n x 192 B,  out : n x 576 B,  status : n x int32 or NULL              */
+int bls381_pairing_batch(const uint8_t* g1, const uint8_t* g2, size_t n, int with_final_exp,
+                         uint8_t* out_fp12, int32_t* status);
+/* same, device pointers, asynchronous on `cuda_stream` (a cudaStream_t cast to void*) */
+int bls381_pairing_batch_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int with_final_exp,
+                             uint8_t* d_out_fp12, void* cuda_stream);
+
+/* Fp12#finalExponentiate()                                      replaces math.ts:856-874
+ *   in / out : n x 576 B                                                                         */
+int bls381_final_exp_batch(const uint8_t* in_fp12, size_t n, uint8_t* out_fp12);
+int bls381_final_exp_batch_dev(const uint8_t* d_in_fp12, size_t n, uint8_t* d_out_fp12, void* cuda_stream);
+
+/* prod_i millerLoop(P_i, Q_i), optionally followed by one shared final exponentiation: the core of
+ * verify (index.ts:763-766) and verifyBatch (index.ts:812-817).
+ *   out : 576 B.  The product over the batch is an exact product in Fp12, so any sharding/ordering of
+ *   the items (warps, CTAs, GPUs) gives the identical 576 bytes.                                   */
+int bls381_miller_product(const uint8_t* g1, const uint8_t* g2, size_t n, int with_final_exp,
+                          uint8_t* out_fp12);
+int bls381_miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int with_final_exp,
+                              uint8_t* d_out_fp12, void* cuda_stream);
+
+/* Generic tower-VM launch (used by the tests and by the entry points above).
+ *   program  : name of a loaded program ("pairing", "miller", "final_exp", ...)
+ *   bufs     : up to 8 DEVICE buffers; strides[i] = bytes per item in buffer i                      */
+int bls381_vm_run_dev(const char* program, uint8_t* const* d_bufs, const uint32_t* strides, int nbuf,
+                      size_t n_items, void* cuda_stream);
+/* Loads a program from memory (file image) under `name`, replacing any previous one. */
+int bls381_vm_load(const char* name, const uint8_t* image, size_t len);
+
+/* Measurement aids (bench.py): number of tower-VM kernel launches since init, and a dependent-free
+ * IMAD.WIDE.U32 issue-rate microbenchmark (returns multiply-adds per second on the whole device). */
+uint64_t bls381_launch_count(void);
+int bls381_imad_peak(double* imad_per_second);
+/* device time in milliseconds of the last tower-VM kernel launched through a host entry point */
+double bls381_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLS381_B200_H */

@@ -1,0 +1,121 @@
+"""ctypes binding of the C ABI (include/bls381_b200.h).  There is no CPU fallback: if the CUDA library
+or a CUDA device is missing, every call raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbls381_b200.so")
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.bls381_init.argtypes = [ctypes.c_int, ctypes.c_char_p]
+    lib.bls381_last_error.restype = ctypes.c_char_p
+    lib.bls381_launch_count.restype = ctypes.c_uint64
+    lib.bls381_last_kernel_ms.restype = ctypes.c_double
+    for name in ("bls381_pairing_batch",):
+        getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_pairing_batch_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_final_exp_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_final_exp_batch_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_miller_product.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    lib.bls381_miller_product_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_vm_run_dev.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_vm_load.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+    lib.bls381_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    return lib
+
+
+EXPORTS = [
+    "bls381_init", "bls381_shutdown", "bls381_last_error", "bls381_sm_count",
+    "bls381_pairing_batch", "bls381_pairing_batch_dev", "bls381_final_exp_batch", "bls381_final_exp_batch_dev",
+    "bls381_miller_product", "bls381_miller_product_dev", "bls381_vm_run_dev", "bls381_vm_load",
+    "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms",
+]
+
+
+class Engine:
+    """Thin object over the C ABI; one per process (the library holds one device context)."""
+
+    def __init__(self, device: int = 0, program_dir: str | None = None):
+        self.lib = _load()
+        rc = self.lib.bls381_init(device, program_dir.encode() if program_dir else None)
+        self._check(rc)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(f"bls381 error {rc}: {self.lib.bls381_last_error().decode()}")
+
+    # ---- host-buffer entry points -------------------------------------------------------------
+    def pairing_batch(self, g1: bytes, g2: bytes, n: int, with_final_exp: bool = True) -> bytes:
+        assert len(g1) == 96 * n and len(g2) == 192 * n
+        out = ctypes.create_string_buffer(576 * n)
+        self._check(self.lib.bls381_pairing_batch(g1, g2, n, int(with_final_exp), out, None))
+        return out.raw
+
+    def final_exp_batch(self, f12: bytes, n: int) -> bytes:
+        assert len(f12) == 576 * n
+        out = ctypes.create_string_buffer(576 * n)
+        self._check(self.lib.bls381_final_exp_batch(f12, n, out))
+        return out.raw
+
+    def miller_product(self, g1: bytes, g2: bytes, n: int, with_final_exp: bool = True) -> bytes:
+        assert len(g1) == 96 * n and len(g2) == 192 * n
+        out = ctypes.create_string_buffer(576)
+        self._check(self.lib.bls381_miller_product(g1, g2, n, int(with_final_exp), out))
+        return out.raw
+
+    # ---- device-pointer entry points (ints = CUDA device addresses, e.g. torch tensor.data_ptr()) ----
+    def pairing_batch_dev(self, d_g1: int, d_g2: int, n: int, with_final_exp: bool, d_out: int, stream: int = 0):
+        self._check(self.lib.bls381_pairing_batch_dev(d_g1, d_g2, n, int(with_final_exp), d_out, stream))
+
+    def final_exp_batch_dev(self, d_in: int, n: int, d_out: int, stream: int = 0):
+        self._check(self.lib.bls381_final_exp_batch_dev(d_in, n, d_out, stream))
+
+    def miller_product_dev(self, d_g1: int, d_g2: int, n: int, with_final_exp: bool, d_out: int, stream: int = 0):
+        self._check(self.lib.bls381_miller_product_dev(d_g1, d_g2, n, int(with_final_exp), d_out, stream))
+
+    def vm_load(self, name: str, image: bytes):
+        self._check(self.lib.bls381_vm_load(name.encode(), image, len(image)))
+
+    def vm_run_dev(self, program: str, bufs, strides, n_items: int, stream: int = 0):
+        nb = len(bufs)
+        arr = (ctypes.c_void_p * nb)(*bufs)
+        st = (ctypes.c_uint32 * nb)(*strides)
+        self._check(self.lib.bls381_vm_run_dev(program.encode(), arr, st, nb, n_items, stream))
+
+    # ---- measurement aids ----------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.bls381_launch_count())
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.bls381_last_kernel_ms())
+
+    def sm_count(self) -> int:
+        return int(self.lib.bls381_sm_count())
+
+    def imad_peak(self) -> float:
+        v = ctypes.c_double(0)
+        self._check(self.lib.bls381_imad_peak(ctypes.byref(v)))
+        return v.value
+
+
+_ENGINE = None
+
+
+def engine(device: int = 0) -> Engine:
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(device)
+    return _ENGINE

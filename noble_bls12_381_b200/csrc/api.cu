@@ -1,0 +1,423 @@
+// C ABI of the engine (include/bls381_b200.h).  Host-side runtime: program registry, device staging
+// pools, launch of the tower-VM kernel, product tree for the multi-Miller entry points.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bls381_b200.h"
+#include "vm_kernel.cu"  // single translation unit: the interpreter kernel
+
+namespace {
+
+struct Program {
+    uint32_t warps = 0, nrec = 0, nconst = 0, nslots = 0, nfar = 0;
+    uint32_t* d_prog = nullptr;
+    uint32_t* d_consts = nullptr;
+};
+
+struct State {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    std::map<std::string, Program> programs;
+    uint32_t* d_far = nullptr;
+    size_t far_bytes = 0;
+    // grow-only device staging for the host entry points
+    uint8_t* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[4] = {0, 0, 0, 0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    std::atomic<uint64_t> launches{0};
+    std::string program_dir;
+};
+
+State g;
+std::mutex g_mu;
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(BLS381_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+constexpr uint32_t kMagic = 0x4D563242u;
+
+int load_image(const std::string& name, const uint8_t* img, size_t len) {
+    if (len < 32) return fail(BLS381_EPROGRAM, "program image too short: " + name);
+    uint32_t h[8];
+    memcpy(h, img, 32);
+    if (h[0] != kMagic || h[1] != 1) return fail(BLS381_EPROGRAM, "bad program magic/version: " + name);
+    Program p;
+    p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6];
+    const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
+    if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
+    if (p.warps != 6 && p.warps != 8 && p.warps != 12) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
+    CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
+    CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p.d_prog, img + 32 + cbytes, pbytes, cudaMemcpyHostToDevice));
+    auto it = g.programs.find(name);
+    if (it != g.programs.end()) {
+        cudaFree(it->second.d_consts);
+        cudaFree(it->second.d_prog);
+    }
+    g.programs[name] = p;
+    return BLS381_OK;
+}
+
+int load_file(const std::string& name) {
+    const std::string path = g.program_dir + "/" + name + ".b2vm";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return fail(BLS381_EPROGRAM, "cannot open " + path + " (run __graft_entry__.build())");
+    std::vector<uint8_t> buf;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize((size_t)n);
+    size_t rd = fread(buf.data(), 1, (size_t)n, f);
+    fclose(f);
+    if (rd != (size_t)n) return fail(BLS381_EPROGRAM, "short read " + path);
+    return load_image(name, buf.data(), buf.size());
+}
+
+int get_program(const char* name, Program** out) {
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    auto it = g.programs.find(name);
+    if (it == g.programs.end()) {
+        int rc = load_file(name);
+        if (rc) return rc;
+        it = g.programs.find(name);
+    }
+    *out = &it->second;
+    return BLS381_OK;
+}
+
+template <int W>
+int launch_w(const vm::Launch& L, int grid, size_t smem, cudaStream_t s) {
+    CUDA_TRY(cudaFuncSetAttribute(vm::vm_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vm::vm_kernel<W><<<grid, W * 32, smem, s>>>(L);
+    CUDA_TRY(cudaGetLastError());
+    return BLS381_OK;
+}
+
+int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int nbuf, size_t n, cudaStream_t s) {
+    if (n == 0) return BLS381_OK;
+    if (n > 0x7fffffffull) return fail(BLS381_EINVAL, "too many items");
+    if (nbuf < 0 || nbuf > vm::kMaxBuffers) return fail(BLS381_EINVAL, "bad buffer count");
+    Program* p = nullptr;
+    int rc = get_program(name, &p);
+    if (rc) return rc;
+    const uint32_t nbatch = (uint32_t)((n + 31) / 32);
+    const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)g.sm_count * 2);
+    const size_t far_need = (size_t)grid * std::max<uint32_t>(p->nfar, 1) * vm::kSlotWords * 4;
+    if (far_need > g.far_bytes) {
+        if (g.d_far) cudaFree(g.d_far);
+        g.d_far = nullptr;
+        g.far_bytes = 0;
+        CUDA_TRY(cudaMalloc(&g.d_far, far_need));
+        g.far_bytes = far_need;
+    }
+    vm::Launch L;
+    memset(&L, 0, sizeof(L));
+    L.prog = p->d_prog;
+    L.consts = p->d_consts;
+    L.nrec = p->nrec;
+    L.nconst = p->nconst;
+    L.nslots = p->nslots;
+    L.nfar = std::max<uint32_t>(p->nfar, 1);
+    L.n_items = (uint32_t)n;
+    L.far = g.d_far;
+    for (int i = 0; i < nbuf; ++i) {
+        L.buf[i].base = bufs[i];
+        L.buf[i].stride = strides[i];
+    }
+    const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48;
+    g.launches.fetch_add(1);
+    switch (p->warps) {
+        case 6: return launch_w<6>(L, grid, smem, s);
+        case 8: return launch_w<8>(L, grid, smem, s);
+        case 12: return launch_w<12>(L, grid, smem, s);
+    }
+    return fail(BLS381_EPROGRAM, "unsupported warp count");
+}
+
+int stage(int k, size_t bytes) {
+    if (bytes > g.stage_bytes[k]) {
+        if (g.d_stage[k]) cudaFree(g.d_stage[k]);
+        g.d_stage[k] = nullptr;
+        g.stage_bytes[k] = 0;
+        size_t cap = std::max<size_t>(bytes, 1 << 20);
+        CUDA_TRY(cudaMalloc(&g.d_stage[k], cap));
+        g.stage_bytes[k] = cap;
+    }
+    return BLS381_OK;
+}
+
+// product tree: d_partials[count x 576] -> d_out (576 B) ; uses d_tmp as ping-pong
+int product_tree(uint8_t* d_a, size_t count, uint8_t* d_b, uint8_t** result, cudaStream_t s) {
+    uint8_t* cur = d_a;
+    uint8_t* nxt = d_b;
+    while (count > 1) {
+        uint8_t* bufs[4] = {nullptr, nullptr, nxt, cur};
+        uint32_t strides[4] = {0, 0, 576, 576};
+        int rc = vm_run("f12_product", bufs, strides, 4, count, s);
+        if (rc) return rc;
+        count = (count + 31) / 32;
+        std::swap(cur, nxt);
+    }
+    *result = cur;
+    return BLS381_OK;
+}
+
+int miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int fe, uint8_t* d_out, cudaStream_t s) {
+    if (n == 0) return fail(BLS381_EINVAL, "empty batch");
+    const size_t nb = (n + 31) / 32;
+    int rc;
+    if ((rc = stage(2, nb * 576))) return rc;
+    if ((rc = stage(3, ((nb + 31) / 32) * 576 + 576))) return rc;
+    uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1), const_cast<uint8_t*>(d_g2), g.d_stage[2]};
+    uint32_t strides[3] = {96, 192, 576};
+    if ((rc = vm_run("miller_product", bufs, strides, 3, n, s))) return rc;
+    uint8_t* res = nullptr;
+    if ((rc = product_tree(g.d_stage[2], nb, g.d_stage[3], &res, s))) return rc;
+    if (fe) {
+        uint8_t* b2[4] = {nullptr, nullptr, d_out, res};
+        uint32_t st2[4] = {0, 0, 576, 576};
+        return vm_run("final_exp", b2, st2, 4, 1, s);
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_out, res, 576, cudaMemcpyDeviceToDevice, s));
+    return BLS381_OK;
+}
+
+// ---- IMAD.WIDE issue-rate microbenchmark -------------------------------------------------------
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters) {
+    uint32_t acc[4][12];
+    uint32_t ct[4] = {0, 0, 0, 0};
+    const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[k][i] = t * 2654435761u + k * 97u + i;
+    uint32_t a0 = t | 1, a1 = t ^ 0x9e3779b9u, a2 = t + 77, a3 = ~t, a4 = t * 3, a5 = t * 5 + 1, b = t * 7 + 3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fpc::chain6(acc[k], ct[k], a0, a1, a2, a3, a4, a5, b);
+        b += ct[0];
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x ^= acc[k][i];
+    out[t] = x ^ ct[1] ^ ct[2] ^ ct[3];
+}
+
+}  // namespace
+
+extern "C" {
+
+int bls381_init(int device, const char* program_dir) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.inited) return BLS381_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BLS381_ENODEV, "no CUDA device: this engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(BLS381_EINVAL, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    if (program_dir && *program_dir) {
+        g.program_dir = program_dir;
+    } else {
+        Dl_info info;
+        if (dladdr((void*)&bls381_init, &info) && info.dli_fname) {
+            std::string p = info.dli_fname;
+            size_t k = p.find_last_of('/');
+            g.program_dir = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/programs";
+        } else {
+            g.program_dir = "programs";
+        }
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&g.ev0));
+    CUDA_TRY(cudaEventCreate(&g.ev1));
+    g.inited = true;
+    return BLS381_OK;
+}
+
+int bls381_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return BLS381_OK;
+    cudaDeviceSynchronize();
+    for (auto& kv : g.programs) {
+        cudaFree(kv.second.d_consts);
+        cudaFree(kv.second.d_prog);
+    }
+    g.programs.clear();
+    if (g.d_far) cudaFree(g.d_far);
+    g.d_far = nullptr;
+    g.far_bytes = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (g.d_stage[k]) cudaFree(g.d_stage[k]);
+        g.d_stage[k] = nullptr;
+        g.stage_bytes[k] = 0;
+    }
+    cudaEventDestroy(g.ev0);
+    cudaEventDestroy(g.ev1);
+    cudaStreamDestroy(g.stream);
+    g.inited = false;
+    return BLS381_OK;
+}
+
+const char* bls381_last_error(void) { return g_err.c_str(); }
+int bls381_sm_count(void) { return g.inited ? g.sm_count : 0; }
+uint64_t bls381_launch_count(void) { return g.launches.load(); }
+double bls381_last_kernel_ms(void) { return g.last_ms; }
+
+int bls381_vm_load(const char* name, const uint8_t* image, size_t len) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!name || !image) return fail(BLS381_EINVAL, "null argument");
+    return load_image(name, image, len);
+}
+
+int bls381_vm_run_dev(const char* program, uint8_t* const* d_bufs, const uint32_t* strides, int nbuf,
+                      size_t n_items, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!program || !d_bufs || !strides) return fail(BLS381_EINVAL, "null argument");
+    return vm_run(program, d_bufs, strides, nbuf, n_items, (cudaStream_t)cuda_stream);
+}
+
+int bls381_pairing_batch_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int with_final_exp,
+                             uint8_t* d_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!d_g1 || !d_g2 || !d_out) return fail(BLS381_EINVAL, "null argument");
+    uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1), const_cast<uint8_t*>(d_g2), d_out};
+    uint32_t strides[3] = {96, 192, 576};
+    return vm_run(with_final_exp ? "pairing" : "miller", bufs, strides, 3, n, (cudaStream_t)cuda_stream);
+}
+
+int bls381_pairing_batch(const uint8_t* g1, const uint8_t* g2, size_t n, int with_final_exp, uint8_t* out,
+                         int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!g1 || !g2 || !out) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    if ((rc = stage(0, n * 96)) || (rc = stage(1, n * 192)) || (rc = stage(2, n * 576))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], g1, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], g2, n * 192, cudaMemcpyHostToDevice, g.stream));
+    uint8_t* bufs[3] = {g.d_stage[0], g.d_stage[1], g.d_stage[2]};
+    uint32_t strides[3] = {96, 192, 576};
+    CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+    if ((rc = vm_run(with_final_exp ? "pairing" : "miller", bufs, strides, 3, n, g.stream))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[2], n * 576, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    if (status) memset(status, 0, n * sizeof(int32_t));
+    return BLS381_OK;
+}
+
+int bls381_final_exp_batch_dev(const uint8_t* d_in, size_t n, uint8_t* d_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!d_in || !d_out) return fail(BLS381_EINVAL, "null argument");
+    uint8_t* bufs[4] = {nullptr, nullptr, d_out, const_cast<uint8_t*>(d_in)};
+    uint32_t strides[4] = {0, 0, 576, 576};
+    return vm_run("final_exp", bufs, strides, 4, n, (cudaStream_t)cuda_stream);
+}
+
+int bls381_final_exp_batch(const uint8_t* in, size_t n, uint8_t* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in || !out) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    if ((rc = stage(0, n * 576)) || (rc = stage(2, n * 576))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * 576, cudaMemcpyHostToDevice, g.stream));
+    uint8_t* bufs[4] = {nullptr, nullptr, g.d_stage[2], g.d_stage[0]};
+    uint32_t strides[4] = {0, 0, 576, 576};
+    CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+    if ((rc = vm_run("final_exp", bufs, strides, 4, n, g.stream))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[2], n * 576, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    return BLS381_OK;
+}
+
+int bls381_miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int with_final_exp,
+                              uint8_t* d_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!d_g1 || !d_g2 || !d_out) return fail(BLS381_EINVAL, "null argument");
+    return miller_product_dev(d_g1, d_g2, n, with_final_exp, d_out, (cudaStream_t)cuda_stream);
+}
+
+int bls381_miller_product(const uint8_t* g1, const uint8_t* g2, size_t n, int with_final_exp, uint8_t* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!g1 || !g2 || !out) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return fail(BLS381_EINVAL, "empty batch");
+    int rc;
+    if ((rc = stage(0, n * 96 + 576)) || (rc = stage(1, n * 192))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0] + 576, g1, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], g2, n * 192, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+    if ((rc = miller_product_dev(g.d_stage[0] + 576, g.d_stage[1], n, with_final_exp, g.d_stage[0], g.stream))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[0], 576, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    return BLS381_OK;
+}
+
+int bls381_imad_peak(double* imad_per_second) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!imad_per_second) return fail(BLS381_EINVAL, "null argument");
+    const int blocks = g.sm_count * 8, threads = 256, iters = 4096;
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, 64);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+        imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, iters);
+        CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+        const double ops = (double)blocks * threads * iters * 24.0;
+        best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaFree(d);
+    *imad_per_second = best;
+    return BLS381_OK;
+}
+
+}  // extern "C"

@@ -34,8 +34,10 @@ static constexpr int kConstSlots = 64;
 
 // ---- record layout -------------------------------------------------------------------------------
 // word 0 (header): [7:0] opcode  [15:8] dst  [19:16] T  [21:20] E  [24:22] ncorr  [25] bar_before
-//                  [26] dst_global  [27] dst_raw (global scratch, no byte swap)  [31:28] reserved
+//                  [26] dst_global  [27] reserved  [28] dst_batch (lane 0 stores at item/32)
+//                  [29] pad_const (padding lanes yield constant aux[31:24])
 // word 1 (aux)   : [7:0] dst buffer id  [15:8] dst field   [23:16] lane xor mask (for XLANE terms)
+//                  [31:24] constant index for pad_const
 // words 2..25    : T terms, 2 words each:
 //     word A: [7:0] xA  [15:8] xB  [19:16] cA (signed 4-bit)  [23:20] cB  [31:24] xflags
 //     word B: [7:0] yA  [15:8] yB  [19:16] cA                [23:20] cB  [31:24] yflags
@@ -48,6 +50,8 @@ enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4 };
 static constexpr uint32_t H_BAR = 1u << 25;
 static constexpr uint32_t H_DSTG = 1u << 26;
 static constexpr uint32_t H_DSTRAW = 1u << 27;
+static constexpr uint32_t H_DSTBATCH = 1u << 28;  // global store by lane 0 only, at index item/32
+static constexpr uint32_t H_PADCONST = 1u << 29;  // lanes beyond n_items produce constant aux[31:24] instead
 
 struct Buffer {
     uint8_t* base;      // device pointer
@@ -76,6 +80,7 @@ struct Ctx {
     uint32_t nslots;
     uint32_t lane;
     uint32_t item;           // global item index of this lane (clamped to n_items-1 for loads)
+    uint32_t batch;          // index of the 32-item batch being processed
     bool store_ok;           // lane < n_items
     const Buffer* buf;
 };
@@ -137,10 +142,11 @@ FPC_DEV void load_wire(uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field
     for (int k = 0; k < 12; ++k) r[k] = bswap32(p[11 - k]);
 }
 
-FPC_DEV void store_wire(const uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field) {
-    if (!c.store_ok) return;
+FPC_DEV void store_wire(const uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field, bool per_batch) {
+    if (per_batch ? (c.lane != 0) : !c.store_ok) return;
     const Buffer& b = c.buf[bufid];
-    uint32_t* p = reinterpret_cast<uint32_t*>(b.base + (size_t)c.item * b.stride + field * 48u);
+    const size_t idx = per_batch ? (size_t)(c.batch) : (size_t)c.item;
+    uint32_t* p = reinterpret_cast<uint32_t*>(b.base + idx * b.stride + field * 48u);
 #pragma unroll
     for (int k = 0; k < 12; ++k) p[11 - k] = bswap32(r[k]);
 }
@@ -218,8 +224,13 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
         (void)fpc::add12(r, r, z);
     }
     fpc::correct(r, ncorr);
+    if ((hdr & H_PADCONST) && !c.store_ok) {
+        const uint32_t* s = c.consts + (aux >> 24) * 12;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = s[k];
+    }
     if (hdr & H_DSTG) {
-        store_wire(r, c, aux & 0xFF, (aux >> 8) & 0xFF);
+        store_wire(r, c, aux & 0xFF, (aux >> 8) & 0xFF, (hdr & H_DSTBATCH) != 0);
     } else {
         store_slot(r, c, dst);
     }

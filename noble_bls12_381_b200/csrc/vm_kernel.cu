@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) vm_kernel(const Launch L) {
         const uint32_t item = batch * 32 + lane;
         c.store_ok = item < L.n_items;
         c.item = c.store_ok ? item : L.n_items - 1;
+        c.batch = batch;
         __syncthreads();  // previous batch fully retired (and constants visible)
         uint32_t next = stream[lane];
         for (uint32_t r = 0; r < L.nrec; ++r) {

@@ -29,7 +29,7 @@ P_OVER_R = P / R  # ~0.1016
 
 OP_NOP, OP_MAC = 0, 1
 F_CONST, F_GLOBAL, F_XLANE = 1, 2, 4
-H_BAR, H_DSTG = 1 << 25, 1 << 26
+H_BAR, H_DSTG, H_DSTBATCH, H_PADCONST = 1 << 25, 1 << 26, 1 << 28, 1 << 29
 REC_WORDS = 32
 MAX_TERMS = 12
 MAX_SUM_BOUND = 80.0  # sum of |x|*|y| bounds in units of p^2 that fits the 768-bit accumulator
@@ -170,6 +170,8 @@ class Op:
     out: Val | None = None
     dst_global: tuple | None = None  # (buf, field)
     xmask: int = 0
+    per_batch: bool = False  # global store by lane 0 at index item/32
+    pad_const: Val | None = None  # padding lanes (item >= n_items) produce this constant instead
     after: list = field(default_factory=list)  # extra ordering deps (Ops)
     step: int = -1
     warp: int = -1
@@ -237,12 +239,23 @@ class Builder:
         # x < 2^384, R2 < p: x*R2/R < 2^384*p/R + p = 2p
         return self._new_op([(x, y)], [], 1).out
 
-    def out(self, e, buf: int, fld: int):
+    def out(self, e, buf: int, fld: int, per_batch=False):
         """Store canonical, out-of-Montgomery value to wire-format output."""
-        v = self.mat(e)
-        x = self._operand(Lin.of(v))
+        if isinstance(e, Lin) and e.is_zero():
+            x = Operand(self.const_raw(0), 1, flags=F_CONST)
+        else:
+            x = self._operand(Lin.of(self.mat(e)))
         y = Operand(self.ONE_PLAIN, 1, flags=F_CONST)
-        return self._new_op([(x, y)], [], 1, dst_global=(buf, fld))
+        op = self._new_op([(x, y)], [], 1, dst_global=(buf, fld))
+        op.per_batch = per_batch
+        return op
+
+    def pad_select(self, e, const_val: Val) -> Val:
+        """Copy of `e` in which padding lanes (items beyond n_items) hold the constant instead."""
+        v = self.mat(e)
+        op = self._new_op([], [Operand(v, 1)], 0)
+        op.pad_const = const_val
+        return op.out
 
     def xlane(self, v: Val, mask: int) -> Val:
         """Value of `v` in lane (lane ^ mask): a copy op with the XLANE operand flag."""
@@ -589,6 +602,11 @@ class Builder:
                     if op.dst_global is not None:
                         hdr |= H_DSTG
                         aux |= op.dst_global[0] | (op.dst_global[1] << 8)
+                        if op.per_batch:
+                            hdr |= H_DSTBATCH
+                    if op.pad_const is not None:
+                        hdr |= H_PADCONST
+                        aux |= op.pad_const.cidx << 24
                     words[0], words[1] = hdr, aux
                     for t, (x, y) in enumerate(op.terms):
                         words[2 + 2 * t] = self._enc_operand(x)

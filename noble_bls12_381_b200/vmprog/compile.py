@@ -1,0 +1,48 @@
+"""Compiles the tower-VM programs into the binary images the C-ABI library loads (*.b2vm).
+
+image := header (8 x u32: magic 'B2VM', version, warps, nrec, nconst, nslots, nfar, reserved)
+         constant table (nconst x 12 u32, Montgomery form)    program (warps x nrec x 32 u32)
+"""
+from __future__ import annotations
+
+import os
+import struct
+import sys
+
+from . import tower
+
+MAGIC = 0x4D563242  # 'B2VM'
+VERSION = 1
+DEFAULT_WARPS = 6
+DEFAULT_SLOTS = 72
+
+
+def image(b) -> bytes:
+    prog, nrec = b.encode()
+    hdr = struct.pack("<8I", MAGIC, VERSION, b.warps, nrec, len(b.consts), b.nslots, b.nfar, 0)
+    return hdr + b.const_table() + prog
+
+
+def compile_program(name: str, warps=DEFAULT_WARPS, nslots=DEFAULT_SLOTS):
+    b = tower.PROGRAMS[name](warps)
+    b.schedule()
+    b.allocate(nslots)
+    b.check_hazards()
+    return b
+
+
+def build_all(outdir: str, warps=DEFAULT_WARPS, nslots=DEFAULT_SLOTS, names=None, verbose=True):
+    os.makedirs(outdir, exist_ok=True)
+    for name in names or tower.PROGRAMS:
+        b = compile_program(name, warps, nslots)
+        path = os.path.join(outdir, name + ".b2vm")
+        with open(path, "wb") as f:
+            f.write(image(b))
+        if verbose:
+            st = b.sched_stats
+            print(f"{name:16s} ops={st['ops']:6d} steps={st['steps']:5d} cost={st['total_cost']:9.0f} "
+                  f"sched_eff={st['efficiency']:.3f} slots={b.peak_slots} far={b.nfar}")
+
+
+if __name__ == "__main__":
+    build_all(sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(__file__)), "programs"))

@@ -421,3 +421,57 @@ def build_fp12_mul_test(warps=6) -> Builder:
     c = _load_f12(b, 4)
     _store_f12(b, (a * c), BUF_OUT)
     return b
+
+
+def _lane_product(b: Builder, t: Tower, f: E12) -> E12:
+    """Butterfly product over the 32 lanes of the CTA (every lane ends with the product of all lanes).
+    Exact in Fp12, so the result is independent of the combination order (index.ts:815)."""
+    for mask in (1, 2, 4, 8, 16):
+        f = f.m(b)
+        other = E12(*[E6(*[E2(Lin.of(b.xlane(b.mat(e2.c0), mask)), Lin.of(b.xlane(b.mat(e2.c1), mask)))
+                           for e2 in (e6.c0, e6.c1, e6.c2)]) for e6 in (f.c0, f.c1)])
+        f = (f * other).m(b)
+    return f
+
+
+def _pad_one(b: Builder, t: Tower, f: E12) -> E12:
+    """Replace the value of padding lanes (items beyond n_items) by Fp12.ONE."""
+    one = b.const(1)
+    zero = b.const_raw(0)
+    flat = f.m(b).flat()
+    sel = [Lin.of(b.pad_select(c if not (isinstance(c, Lin) and c.is_zero()) else Lin.of(zero), one if k == 0 else zero))
+           for k, c in enumerate(flat)]
+    e2 = [E2(sel[2 * i], sel[2 * i + 1]) for i in range(6)]
+    return E12(E6(e2[0], e2[1], e2[2]), E6(e2[3], e2[4], e2[5]))
+
+
+def build_miller_product(warps=6) -> Builder:
+    """One Fp12 per 32-item batch: prod_lanes millerLoop(P_i, Q_i) (padding lanes contribute ONE)."""
+    b = Builder(warps)
+    t = Tower(b)
+    Px, Py, Qx, Qy = _load_g1_g2(b)
+    f = t.miller_loop(Px, Py, Qx, Qy)
+    f = _lane_product(b, t, _pad_one(b, t, f))
+    for k, c in enumerate(f.flat()):
+        b.out(c, BUF_OUT, k, per_batch=True)
+    return b
+
+
+def build_f12_product(warps=6) -> Builder:
+    """One Fp12 per 32-item batch: product of the batch's Fp12 inputs (second level of the tree)."""
+    b = Builder(warps)
+    t = Tower(b)
+    f = _lane_product(b, t, _pad_one(b, t, _load_f12(b)))
+    for k, c in enumerate(f.flat()):
+        b.out(c, BUF_OUT, k, per_batch=True)
+    return b
+
+
+PROGRAMS = {
+    "pairing": lambda w: build_pairing(w, True),
+    "miller": lambda w: build_pairing(w, False),
+    "final_exp": build_final_exp,
+    "miller_product": build_miller_product,
+    "f12_product": build_f12_product,
+    "f12_mul_test": build_fp12_mul_test,
+}

@@ -1,0 +1,142 @@
+"""CPU tests of the product's host logic: Fp carry-chain core (portable backend), tower-VM program
+builder / scheduler / slot allocator / encoder, validated through the CPU emulation of the interpreter
+(tests/emu) against the oracle.  No GPU needed."""
+import ctypes
+import os
+import random
+
+import pytest
+
+from noble_bls12_381_b200 import synth
+from noble_bls12_381_b200.vmprog import compile as vmcompile
+from oracle import noble_oracle as O
+from tests.emu import emu
+
+R = 1 << 384
+RINV = pow(R, -1, O.P)
+
+
+def _limbs(x):
+    return (ctypes.c_uint32 * 12)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
+
+
+def _val(a):
+    return sum(int(a[i]) << (32 * i) for i in range(12))
+
+
+def test_fp_core_mont_mul_and_lazy_mac():
+    L = emu.lib()
+    rng = random.Random(1)
+    edge = [0, 1, O.P - 1, O.P - 2, (1 << 381) - 1, 2**32 - 1, 2**64, O.P // 2]
+    cases = [(a, b) for a in edge for b in edge] + [(rng.randrange(O.P), rng.randrange(O.P)) for _ in range(500)]
+    for a, b in cases:
+        r = (ctypes.c_uint32 * 12)()
+        L.emu_mont_mul(_limbs(a), _limbs(b), r)
+        assert _val(r) == a * b * RINV % O.P
+    for _ in range(200):
+        n = rng.randint(1, 12)
+        bound = rng.choice([1, 2, 4])
+        A = [rng.randrange(bound * O.P) for _ in range(n)]
+        B = [rng.randrange(bound * O.P) for _ in range(n)]
+        S = sum(x * y for x, y in zip(A, B))
+        K = S // (R * O.P) + 2
+        rounds = (K - 1).bit_length()
+        if S >= 80 * O.P * O.P or rounds > 3:
+            continue
+        aa = (ctypes.c_uint32 * (12 * n))(*[(A[i] >> (32 * k)) & 0xFFFFFFFF for i in range(n) for k in range(12)])
+        bb = (ctypes.c_uint32 * (12 * n))(*[(B[i] >> (32 * k)) & 0xFFFFFFFF for i in range(n) for k in range(12)])
+        r = (ctypes.c_uint32 * 12)()
+        L.emu_mac_redc(n, aa, bb, rounds, r)
+        assert _val(r) == S * RINV % O.P
+
+
+def _random_pairs(n, seed):
+    rng = random.Random(seed)
+    pts = []
+    for _ in range(n):
+        a, c = rng.randrange(1, O.R_ORDER), rng.randrange(1, O.R_ORDER)
+        pts.append((O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, a)),
+                    O.pt_to_affine(O.G2, O.pt_multiply_unsafe(O.G2, O.G2_BASE, c))))
+    g1 = bytearray(b"".join(p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big") for p, _ in pts))
+    g2 = bytearray(b"".join(b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1])) for _, q in pts))
+    return pts, g1, g2
+
+
+def _miller(p, q):
+    return O.miller_loop(O.calc_pairing_precomputes(*q), p)
+
+
+@pytest.fixture(scope="module")
+def programs():
+    return {n: vmcompile.compile_program(n) for n in ("pairing", "miller", "final_exp", "miller_product", "f12_product")}
+
+
+def test_programs_schedule_and_slots(programs):
+    for name, b in programs.items():
+        b.check_hazards()
+        assert b.peak_slots <= b.nslots and b.nslots + b.nfar <= 255
+        assert b.sched_stats["efficiency"] > 0.5
+        # every warp stream has the same number of barriers by construction; image size is consistent
+        img = vmcompile.image(b)
+        nrec = int.from_bytes(img[12:16], "little")
+        assert len(img) == 32 + 48 * len(b.consts) + b.warps * nrec * 128
+
+
+def test_pairing_program_bit_exact_on_emulator(programs):
+    n = 35  # two batches, the second one ragged
+    pts, g1, g2 = _random_pairs(n, 5)
+    out = bytearray(576 * n)
+    emu.run_program(programs["pairing"], {0: (g1, 96), 1: (g2, 192), 2: (out, 576)}, n)
+    mil = bytearray(576 * n)
+    emu.run_program(programs["miller"], {0: (g1, 96), 1: (g2, 192), 2: (mil, 576)}, n)
+    for i, (p, q) in enumerate(pts):
+        f = _miller(p, q)
+        assert bytes(mil[576 * i : 576 * i + 576]) == O.fp12_to_bytes(f)  # pairing(P, Q, false)
+        assert bytes(out[576 * i : 576 * i + 576]) == O.fp12_to_bytes(O.fp12_final_exponentiate(f))
+
+
+def test_kilic_prefix_on_emulator(programs, golden_dir):
+    n = 8
+    g1, g2 = synth.multiples_wire(n)
+    out = bytearray(576 * n)
+    emu.run_program(programs["pairing"], {0: (bytearray(g1), 96), 1: (bytearray(g2), 192), 2: (out, 576)}, n)
+    gold = open(os.path.join(golden_dir, "pairing_kilic_1000.bin"), "rb").read()
+    assert bytes(out) == gold[: 576 * n]
+
+
+def test_final_exp_kat_on_emulator(programs, golden_dir):
+    import json
+    k = json.load(open(os.path.join(golden_dir, "pairing_kats.json")))
+    fin = O.fp12_from_twelve([int(x, 16) for x in k["final_exp_in"]])
+    out = bytearray(576)
+    emu.run_program(programs["final_exp"], {2: (out, 576), 3: (bytearray(O.fp12_to_bytes(fin)), 576)}, 1)
+    assert [int.from_bytes(out[48 * i : 48 * i + 48], "big") for i in range(12)] == [int(x, 16) for x in k["final_exp_out"]]
+
+
+def test_product_tree_programs_on_emulator(programs):
+    n = 37
+    pts, g1, g2 = _random_pairs(n, 7)
+    part = bytearray(576 * 2)
+    emu.run_program(programs["miller_product"], {0: (g1, 96), 1: (g2, 192), 2: (part, 576)}, n)
+    mill = [_miller(p, q) for p, q in pts]
+
+    def prod(fs):
+        r = O.FP12_ONE
+        for f in fs:
+            r = O.fp12_mul(r, f)
+        return r
+
+    assert bytes(part[:576]) == O.fp12_to_bytes(prod(mill[:32]))
+    assert bytes(part[576:]) == O.fp12_to_bytes(prod(mill[32:]))
+    out = bytearray(576)
+    emu.run_program(programs["f12_product"], {2: (out, 576), 3: (part, 576)}, 2)
+    assert bytes(out) == O.fp12_to_bytes(prod(mill))
+
+
+def test_synth_matches_oracle_multiples():
+    g1, g2 = synth.multiples_wire(5)
+    for i in range(5):
+        p = O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, i + 1))
+        q = O.pt_to_affine(O.G2, O.pt_multiply_unsafe(O.G2, O.G2_BASE, i + 1))
+        assert g1[96 * i : 96 * i + 96] == p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+        assert g2[192 * i : 192 * i + 192] == b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
