@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--n", type=int, default=65536, help="pairings per step per GPU")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--program-dir", default=None, help="alternative tower-VM program directory (tuning)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -134,7 +135,7 @@ def main():
 
     import noble_bls12_381_b200 as bls
     from noble_bls12_381_b200 import synth
-    eng = bls.Engine(local_rank)
+    eng = bls.Engine(local_rank, args.program_dir)
     n = args.n
     # synthetic inputs: (i*G1, i*G2); every rank processes its own n items (weak scaling, sharded by index)
     t_gen = time.time()

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -38,6 +39,7 @@ struct State {
     double last_ms = 0.0;
     std::atomic<uint64_t> launches{0};
     std::string program_dir;
+    int force_ctas = 0;  // tuning override (env BLS381_B200_CTAS)
 };
 
 State g;
@@ -67,7 +69,7 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6];
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
-    if (p.warps != 6 && p.warps != 8 && p.warps != 12) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    if (p.warps != 6 && p.warps != 8) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
@@ -108,10 +110,10 @@ int get_program(const char* name, Program** out) {
     return BLS381_OK;
 }
 
-template <int W>
+template <int W, int MINB>
 int launch_w(const vm::Launch& L, int grid, size_t smem, cudaStream_t s) {
-    CUDA_TRY(cudaFuncSetAttribute(vm::vm_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vm::vm_kernel<W><<<grid, W * 32, smem, s>>>(L);
+    CUDA_TRY(cudaFuncSetAttribute(vm::vm_kernel<W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vm::vm_kernel<W, MINB><<<grid, W * 32, smem, s>>>(L);
     CUDA_TRY(cudaGetLastError());
     return BLS381_OK;
 }
@@ -124,7 +126,10 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     int rc = get_program(name, &p);
     if (rc) return rc;
     const uint32_t nbatch = (uint32_t)((n + 31) / 32);
-    const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)g.sm_count * 2);
+    const size_t smem_est = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 1024;
+    int ctas_per_sm = std::max(1, std::min(p->warps == 6 ? 3 : 2, (int)(232448 / smem_est)));
+    if (g.force_ctas > 0) ctas_per_sm = std::min(ctas_per_sm, g.force_ctas);
+    const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)(g.sm_count * ctas_per_sm));
     const size_t far_need = (size_t)grid * std::max<uint32_t>(p->nfar, 1) * vm::kSlotWords * 4;
     if (far_need > g.far_bytes) {
         if (g.d_far) cudaFree(g.d_far);
@@ -147,13 +152,10 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
         L.buf[i].base = bufs[i];
         L.buf[i].stride = strides[i];
     }
-    const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48;
+    const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64;  // slots + constants + progress counters
     g.launches.fetch_add(1);
-    switch (p->warps) {
-        case 6: return launch_w<6>(L, grid, smem, s);
-        case 8: return launch_w<8>(L, grid, smem, s);
-        case 12: return launch_w<12>(L, grid, smem, s);
-    }
+    if (p->warps == 6) return ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
+    if (p->warps == 8) return launch_w<8, 2>(L, grid, smem, s);
     return fail(BLS381_EPROGRAM, "unsupported warp count");
 }
 
@@ -207,13 +209,13 @@ int miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int f
 
 // ---- IMAD.WIDE issue-rate microbenchmark -------------------------------------------------------
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters) {
-    uint32_t acc[4][12];
+    uint64_t acc[4][6];
     uint32_t ct[4] = {0, 0, 0, 0};
     const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) acc[k][i] = t * 2654435761u + k * 97u + i;
+        for (int i = 0; i < 6; ++i) acc[k][i] = ((uint64_t)(t * 2654435761u + k * 97u + i) << 32) | (t + i);
     uint32_t a0 = t | 1, a1 = t ^ 0x9e3779b9u, a2 = t + 77, a3 = ~t, a4 = t * 3, a5 = t * 5 + 1, b = t * 7 + 3;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) x ^= acc[k][i];
+        for (int i = 0; i < 6; ++i) x ^= (uint32_t)acc[k][i] ^ (uint32_t)(acc[k][i] >> 32);
     out[t] = x ^ ct[1] ^ ct[2] ^ ct[3];
 }
 
@@ -256,6 +258,7 @@ int bls381_init(int device, const char* program_dir) {
             g.program_dir = "programs";
         }
     }
+    if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g.ev0));
     CUDA_TRY(cudaEventCreate(&g.ev1));

@@ -4,7 +4,7 @@
 // followed by `%`, math.ts:80-83) with register-resident carry chains:
 //   * acc_mac   : 768-bit accumulator += a*b       (144 IMAD.WIDE.U32[.X], no reduction)
 //   * acc_redc  : Montgomery reduction of the accumulator (12 x (1 IMAD + 12 IMAD.WIDE.U32.X))
-//   * add12/sub12/csub: carry-chain add/sub and conditional subtraction of k*p
+//   * add12/sub12/csub_kp: carry-chain add/sub and conditional subtraction of k*p (immediates)
 // "Lazy reduction": tower formulas accumulate many products into one accumulator and reduce once.
 //
 // The generated primitives also have a portable C++ body (`#else` of __CUDA_ARCH__) used ONLY by the CPU
@@ -26,9 +26,9 @@ namespace fpc {
 
 FPC_DEV void acc_zero(Acc& A) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) A.e[i] = 0;
+    for (int i = 0; i < 12; ++i) A.e[i] = 0;
 #pragma unroll
-    for (int i = 0; i < 22; ++i) A.o[i] = 0;
+    for (int i = 0; i < 11; ++i) A.o[i] = 0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) A.c[i] = 0;
 }
@@ -43,23 +43,12 @@ FPC_DEV void zero12(uint32_t* r) {
     for (int i = 0; i < 12; ++i) r[i] = 0;
 }
 
-// r = (r >= kp) ? r - kp : r      (kp = table of k*p)
-FPC_DEV void csub(uint32_t* r, const uint32_t* kp) {
-    uint32_t t[12];
-    uint32_t borrow = sub12(t, r, kp);
-#pragma unroll
-    for (int i = 0; i < 12; ++i) r[i] = borrow ? r[i] : t[i];
-}
-
 // bring a value < 2^rounds * p (rounds <= 3) into [0, p)
 FPC_DEV void correct(uint32_t* r, int rounds) {
-    if (rounds >= 3) csub(r, kP4);
-    if (rounds >= 2) csub(r, kP2);
-    if (rounds >= 1) csub(r, kP1);
+    if (rounds >= 3) csub_4p(r);
+    if (rounds >= 2) csub_2p(r);
+    if (rounds >= 1) csub_1p(r);
 }
-
-// r = p - a   (a in [0,p] -> r in [0,p]; NOT canonical for a == 0, fine as a multiplicand)
-FPC_DEV void neg_raw(uint32_t* r, const uint32_t* a) { (void)sub12(r, kP1, a); }
 
 // Montgomery product, canonical output: r = a*b/R mod p  (a, b < p)
 FPC_DEV void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
@@ -67,13 +56,13 @@ FPC_DEV void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     acc_zero(A);
     acc_mac(A, a, b);
     acc_redc(A, r);
-    csub(r, kP1);
+    csub_1p(r);
 }
 
 // r = a + b mod p, a, b canonical
 FPC_DEV void add_mod(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     (void)add12(r, a, b);
-    csub(r, kP1);
+    csub_1p(r);
 }
 
 // r = a - b mod p, a, b canonical

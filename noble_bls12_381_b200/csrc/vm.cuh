@@ -33,7 +33,7 @@ static constexpr int kMaxBuffers = 8;
 static constexpr int kConstSlots = 64;
 
 // ---- record layout -------------------------------------------------------------------------------
-// word 0 (header): [7:0] opcode  [15:8] dst  [19:16] T  [21:20] E  [24:22] ncorr  [25] bar_before
+// word 0 (header): [7:0] opcode  [15:8] dst  [19:16] T  [21:20] E  [24:22] ncorr  [25] has_waits
 //                  [26] dst_global  [27] reserved  [28] dst_batch (lane 0 stores at item/32)
 //                  [29] pad_const (padding lanes yield constant aux[31:24])
 // word 1 (aux)   : [7:0] dst buffer id  [15:8] dst field   [23:16] lane xor mask (for XLANE terms)
@@ -41,12 +41,15 @@ static constexpr int kConstSlots = 64;
 // words 2..25    : T terms, 2 words each:
 //     word A: [7:0] xA  [15:8] xB  [19:16] cA (signed 4-bit)  [23:20] cB  [31:24] xflags
 //     word B: [7:0] yA  [15:8] yB  [19:16] cA                [23:20] cB  [31:24] yflags
-// words 26..29   : E epilogue operands, same 1-word operand encoding in words 26 and 28 (27/29 spare)
+// words 26, 28   : E epilogue operands (same 1-word operand encoding)
+// words 27,29,30,31: eight 16-bit progress requirements (warp 0..7): this record may start only when
+//                  warp w has completed at least that many records of its stream (0 = no requirement)
 // operand flags  : bit0 CONST  (A/B index the constant table instead of slots)
 //                  bit1 GLOBAL (A = buffer id, B = field index: wire-format big-endian 48-byte field)
 //                  bit2 XLANE  (read the slot column of lane ^ mask)
+//                  bit3 SIMPLE (operand is exactly one shared-memory slot, coefficient +1: fast path)
 enum : uint32_t { OP_NOP = 0, OP_MAC = 1 };
-enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4 };
+enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8 };
 static constexpr uint32_t H_BAR = 1u << 25;
 static constexpr uint32_t H_DSTG = 1u << 26;
 static constexpr uint32_t H_DSTRAW = 1u << 27;
@@ -173,8 +176,26 @@ FPC_DEV void load_one(uint32_t* r, const Ctx& c, uint32_t idx, uint32_t flags, u
     }
 }
 
+FPC_DEV void load_near(uint32_t* r, const Ctx& c, uint32_t slot) {
+    const uint32_t* s = c.slots + slot * kSlotWords + c.lane * 4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
+        r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+    }
+#else
+    for (int q = 0; q < 3; ++q)
+        for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
+#endif
+}
+
 // operand = cA*A + cB*B  (negative coefficients via p - X), unreduced
 FPC_DEV void load_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask) {
+    if (w & (F_SIMPLE << 24)) {
+        load_near(r, c, w & 0xFF);
+        return;
+    }
     const uint32_t a = w & 0xFF, b = (w >> 8) & 0xFF, flags = w >> 24;
     const int ca = sext4(w >> 16), cb = sext4(w >> 20);
     if (flags & F_GLOBAL) {

@@ -4,12 +4,21 @@
 
 namespace vm {
 
-// Persistent CTAs: each CTA loops over batches of 32 items (lane = item).
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) vm_kernel(const Launch L) {
+__device__ __forceinline__ void wait_progress(const volatile uint32_t* progress, uint32_t w, uint32_t need) {
+    if (need == 0) return;
+    while (progress[w] < need) {
+    }
+}
+
+// Persistent CTAs: each CTA loops over batches of 32 items (lane = item).  Inside a batch there are NO
+// CTA-wide barriers: a warp runs its own record stream and waits only for the progress counters its next
+// record names (static dataflow schedule, see vmprog/builder.py).
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     extern __shared__ uint4 smem_raw[];
     uint32_t* slots = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* sconst = slots + (size_t)L.nslots * kSlotWords;
+    volatile uint32_t* progress = sconst + (size_t)L.nconst * 12;  // [16]
     for (uint32_t i = threadIdx.x; i < L.nconst * 12; i += blockDim.x) sconst[i] = L.consts[i];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -30,20 +39,36 @@ __global__ void __launch_bounds__(WARPS * 32, 2) vm_kernel(const Launch L) {
         c.item = c.store_ok ? item : L.n_items - 1;
         c.batch = batch;
         __syncthreads();  // previous batch fully retired (and constants visible)
+        if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+        __syncthreads();
         uint32_t next = stream[lane];
         for (uint32_t r = 0; r < L.nrec; ++r) {
             const uint32_t cur = next;
             if (r + 1 < L.nrec) next = stream[(size_t)(r + 1) * kRecWords + lane];  // prefetch
             const uint32_t hdr = __shfl_sync(0xffffffffu, cur, 0);
             const uint32_t aux = __shfl_sync(0xffffffffu, cur, 1);
-            if (hdr & H_BAR) __syncthreads();
+            if (hdr & H_BAR) {  // this record carries progress requirements
+                const uint32_t w01 = __shfl_sync(0xffffffffu, cur, 27), w23 = __shfl_sync(0xffffffffu, cur, 29);
+                const uint32_t w45 = __shfl_sync(0xffffffffu, cur, 30), w67 = __shfl_sync(0xffffffffu, cur, 31);
+                wait_progress(progress, 0, w01 & 0xFFFF); wait_progress(progress, 1, w01 >> 16);
+                wait_progress(progress, 2, w23 & 0xFFFF); wait_progress(progress, 3, w23 >> 16);
+                wait_progress(progress, 4, w45 & 0xFFFF); wait_progress(progress, 5, w45 >> 16);
+                wait_progress(progress, 6, w67 & 0xFFFF); wait_progress(progress, 7, w67 >> 16);
+                __threadfence_block();
+                __syncwarp();
+            }
             exec_record(c, hdr, aux, [&](uint32_t i) { return __shfl_sync(0xffffffffu, cur, i); });
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                progress[warp] = r + 1;
+            }
         }
     }
 }
 
-template __global__ void vm_kernel<6>(const Launch);
-template __global__ void vm_kernel<8>(const Launch);
-template __global__ void vm_kernel<12>(const Launch);
+template __global__ void vm_kernel<6, 2>(const Launch);
+template __global__ void vm_kernel<6, 3>(const Launch);
+template __global__ void vm_kernel<8, 2>(const Launch);
 
 }  // namespace vm

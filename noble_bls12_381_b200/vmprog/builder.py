@@ -28,7 +28,7 @@ R2_MOD_P = R * R % P
 P_OVER_R = P / R  # ~0.1016
 
 OP_NOP, OP_MAC = 0, 1
-F_CONST, F_GLOBAL, F_XLANE = 1, 2, 4
+F_CONST, F_GLOBAL, F_XLANE, F_SIMPLE = 1, 2, 4, 8
 H_BAR, H_DSTG, H_DSTBATCH, H_PADCONST = 1 << 25, 1 << 26, 1 << 28, 1 << 29
 REC_WORDS = 32
 MAX_TERMS = 12
@@ -175,11 +175,14 @@ class Op:
     after: list = field(default_factory=list)  # extra ordering deps (Ops)
     step: int = -1
     warp: int = -1
+    sidx: int = -1
     tag: str = ""
 
     def cost(self):
+        """Estimated duration in units of one 12x12 product (calibrated on the ncu instruction counts: a
+        product ~300 issued instructions, per-op reduction/correction/decode overhead ~500)."""
         t = len(self.terms)
-        return (t + 1.1 if t else 0.0) + 0.35 + 0.1 * len(self.epi)
+        return (t + 1.7 if t else 0.6) + 0.1 * len(self.epi)
 
     def src_vals(self):
         vs = []
@@ -433,8 +436,13 @@ class Builder:
 
     # ------------------------------------------------------------------------------------------
     def schedule(self):
-        """Level-based list scheduling: a step holds ops whose producers finished in earlier steps;
-        ops of a step are packed onto the warps longest-first.  Returns list of steps (lists per warp)."""
+        """Static dataflow list scheduling onto the W warps of a CTA.
+
+        There are no CTA-wide barriers: every warp executes its own stream in order and, before a record,
+        waits until the other warps' progress counters (number of completed records) reach the values the
+        record carries.  Here: (1) priorities = longest path to a sink, (2) event-driven list scheduling with
+        an estimated duration per micro-op, (3) the resulting start times define one linear order L; each
+        warp's stream is its ops in L order."""
         W = self.warps
         n = len(self.ops)
         deps = [set() for _ in range(n)]
@@ -447,133 +455,195 @@ class Builder:
         for i in range(n):
             for d in deps[i]:
                 users[d].append(i)
-        # priority = longest path to a sink
+        cost = [op.cost() for op in self.ops]
         prio = [0.0] * n
         for i in range(n - 1, -1, -1):
-            c = self.ops[i].cost()
-            prio[i] = c + max((prio[u] for u in users[i]), default=0.0)
+            prio[i] = cost[i] + max((prio[u] for u in users[i]), default=0.0)
         remaining = [len(d) for d in deps]
+        est = [0.0] * n  # earliest start (all producers finished)
+        finish = [0.0] * n
+        start = [0.0] * n
         ready = [i for i in range(n) if remaining[i] == 0]
-        steps = []
+        warp_free = [0.0] * W
         scheduled = 0
         while scheduled < n:
             assert ready, "dependency cycle"
-            ready.sort(key=lambda i: -prio[i])
-            maxprio = prio[ready[0]]
-            # urgent ops define the step length; the rest only fill idle capacity
-            bins = [0.0] * W
-            assign = [[] for _ in range(W)]
-            chosen = []
-            urgent = [i for i in ready if prio[i] >= maxprio - 1e-9 or True]
-            total = sum(self.ops[i].cost() for i in urgent)
-            cap = max(total / W, max(self.ops[i].cost() for i in urgent))
-            for i in sorted(ready, key=lambda i: -self.ops[i].cost()):
-                b = min(range(W), key=lambda k: bins[k])
-                c = self.ops[i].cost()
-                if bins[b] > 0 and bins[b] + c > cap * 1.05:
-                    continue
-                bins[b] += c
-                assign[b].append(i)
-                chosen.append(i)
-            step_idx = len(steps)
-            for w in range(W):
-                for i in assign[w]:
-                    self.ops[i].step = step_idx
-                    self.ops[i].warp = w
-            steps.append(assign)
-            scheduled += len(chosen)
-            cs = set(chosen)
-            ready = [i for i in ready if i not in cs]
-            for i in chosen:
-                for u in users[i]:
-                    remaining[u] -= 1
-                    if remaining[u] == 0:
-                        ready.append(u)
-        self.steps = steps
-        loads = [max(sum(self.ops[i].cost() for i in wl) for wl in st) for st in steps]
-        total = sum(op.cost() for op in self.ops)
+            w = min(range(W), key=lambda k: warp_free[k])
+            t = warp_free[w]
+            avail = [i for i in ready if est[i] <= t + 1e-9]
+            if avail:
+                i = max(avail, key=lambda k: prio[k])
+            else:
+                i = min(ready, key=lambda k: (est[k], -prio[k]))
+                t = est[i]
+            ready.remove(i)
+            start[i] = t
+            finish[i] = t + cost[i]
+            warp_free[w] = finish[i]
+            self.ops[i].warp = w
+            scheduled += 1
+            for u in users[i]:
+                remaining[u] -= 1
+                est[u] = max(est[u], finish[i])
+                if remaining[u] == 0:
+                    ready.append(u)
+        order = sorted(range(n), key=lambda i: (start[i], i))
+        self.order = order
+        self.pos = {i: k for k, i in enumerate(order)}  # position in the linear order L
+        self.streams = [[] for _ in range(W)]
+        for i in order:
+            op = self.ops[i]
+            op.step = self.pos[i]
+            op.sidx = len(self.streams[op.warp])  # index in its warp's stream
+            self.streams[op.warp].append(i)
+        makespan = max(finish) if n else 0.0
+        total = sum(cost)
         self.sched_stats = {
             "ops": n,
-            "steps": len(steps),
+            "steps": n,
             "total_cost": total,
-            "critical_cost": sum(loads),
-            "efficiency": total / (W * sum(loads)) if loads else 1.0,
+            "critical_cost": makespan,
+            "efficiency": total / (W * makespan) if makespan else 1.0,
         }
-        return steps
+        return self.streams
 
     # ------------------------------------------------------------------------------------------
-    def allocate(self, nslots: int, nfar_max: int = 160):
-        """Step-accurate slot allocation.  A value occupies its slot from its defining step to its last
-        reading step; a slot may be re-written only in a step strictly after the last read."""
+    def allocate(self, nslots: int, nfar_max: int = 180):
+        """Slot allocation along the linear order L.  A value occupies its slot from its definition to its
+        last reader (positions in L); a slot is re-written only by an op later in L than every reader of the
+        previous value, and that op WAITS for those readers (WAR) -- see `_compute_waits`."""
         last_use = {}
+        readers = {}
         for op in self.ops:
             for v in op.src_vals():
                 last_use[v.id] = max(last_use.get(v.id, -1), op.step)
+                readers.setdefault(v.id, []).append(op.id)
+        self.readers = readers
         defs = [op for op in self.ops if op.out is not None]
         for op in defs:
-            last_use.setdefault(op.out.id, op.step)  # dead value: free right after
-        # choose far values: repeatedly move the longest-lived values out until pressure fits
-        nsteps = len(self.steps)
+            last_use.setdefault(op.out.id, op.step)
+        npos = len(self.ops)
         far = set()
+        uses = {vid: len(r) for vid, r in readers.items()}
 
         def pressure():
-            delta = [0] * (nsteps + 2)
+            delta = [0] * (npos + 2)
             for op in defs:
                 if op.out.id in far:
                     continue
                 delta[op.step] += 1
                 delta[last_use[op.out.id] + 1] -= 1
-            cur, peak, prof = 0, 0, []
-            for s in range(nsteps + 1):
-                cur += delta[s]
-                prof.append(cur)
-                peak = max(peak, cur)
-            return peak, prof
+            cur, peak, at = 0, 0, 0
+            for s_ in range(npos + 1):
+                cur += delta[s_]
+                if cur > peak:
+                    peak, at = cur, s_
+            return peak, at
 
-        peak, prof = pressure()
+        peak, at = pressure()
         while peak > nslots:
-            # among values live at the peak step, evict the one with the fewest uses per lifetime
-            s_peak = prof.index(peak)
-            uses = {}
-            for op in self.ops:
-                for v in op.src_vals():
-                    uses[v.id] = uses.get(v.id, 0) + 1
-            cands = [op for op in defs if op.out.id not in far and op.step <= s_peak <= last_use[op.out.id]]
+            cands = [op for op in defs if op.out.id not in far and op.step <= at <= last_use[op.out.id]]
             cands.sort(key=lambda op: (last_use[op.out.id] - op.step) / (1 + uses.get(op.out.id, 0)), reverse=True)
             far.add(cands[0].out.id)
-            peak, prof = pressure()
+            peak, at = pressure()
         self.peak_slots = peak
+        nslots = max(peak, 1)  # never reserve more shared memory than the program needs
         slot_of = {}
-        free_at = [0] * nslots  # first step in which the slot may be written again
-        far_free_at = []
-        by_step = sorted(defs, key=lambda op: (op.step, op.id))
-        for op in by_step:
+        import heapq
+        free_near = [(0, k) for k in range(nslots)]  # (position at which it became free, slot): LRU first
+        heapq.heapify(free_near)
+        free_far = []
+        nfar = 0
+        busy = []  # heap of (last_use, slot, is_far)
+        self.prev_in_slot = {}  # op id -> value id previously held by the slot it writes
+        cur_val = {}
+        for op in sorted(defs, key=lambda o: o.step):
+            while busy and busy[0][0] < op.step:
+                lu, k, isfar = heapq.heappop(busy)
+                heapq.heappush(free_far if isfar else free_near, (lu, k))
             vid = op.out.id
-            lu = last_use[vid]
             if vid in far:
-                for k in range(len(far_free_at)):
-                    if far_free_at[k] <= op.step:
-                        far_free_at[k] = lu + 1
-                        slot_of[vid] = nslots + k
-                        break
+                if free_far:
+                    _, k = heapq.heappop(free_far)
                 else:
-                    far_free_at.append(lu + 1)
-                    slot_of[vid] = nslots + len(far_free_at) - 1
+                    k = nslots + nfar
+                    nfar += 1
+                heapq.heappush(busy, (last_use[vid], k, True))
             else:
-                for k in range(nslots):
-                    if free_at[k] <= op.step:
-                        free_at[k] = lu + 1
-                        slot_of[vid] = k
-                        break
-                else:
-                    raise AssertionError("slot allocation failed despite pressure check")
+                assert free_near, "slot allocation failed despite pressure check"
+                _, k = heapq.heappop(free_near)
+                heapq.heappush(busy, (last_use[vid], k, False))
+            slot_of[vid] = k
+            if k in cur_val:
+                self.prev_in_slot[op.id] = cur_val[k]
+            cur_val[k] = vid
         self.nslots = nslots
-        self.nfar = len(far_free_at)
+        self.nfar = nfar
         assert self.nfar <= nfar_max and nslots + self.nfar <= 255, (self.nfar, nslots)
         self.slot_of = slot_of
+        self._compute_waits()
         return slot_of
 
-    # ------------------------------------------------------------------------------------------
+    def _compute_waits(self):
+        """Per record: the progress each other warp must have reached (RAW on operands, WAR/WAW on the
+        destination slot).  Requirements already implied by earlier records of the same warp are dropped."""
+        W = self.warps
+        val_op = {op.out.id: op for op in self.ops if op.out is not None}
+        known = [[0] * W for _ in range(W)]
+        self.waits = {}
+        self.full_reqs = {}
+        for i in self.order:
+            op = self.ops[i]
+            req = [0] * W
+            for v in op.src_vals():
+                y = v.op
+                req[y.warp] = max(req[y.warp], y.sidx + 1)
+            for a in op.after:
+                req[a.warp] = max(req[a.warp], a.sidx + 1)
+            pv = self.prev_in_slot.get(i)
+            if pv is not None:
+                y = val_op[pv]
+                req[y.warp] = max(req[y.warp], y.sidx + 1)
+                for zid in self.readers.get(pv, []):
+                    z = self.ops[zid]
+                    req[z.warp] = max(req[z.warp], z.sidx + 1)
+            req[op.warp] = 0
+            self.full_reqs[i] = list(req)
+            k = known[op.warp]
+            emit = [r if r > k[w2] else 0 for w2, r in enumerate(req)]
+            for w2, r in enumerate(req):
+                k[w2] = max(k[w2], r)
+            self.waits[i] = emit
+
+    def check_hazards(self):
+        """Vector-clock proof that the emitted waits order every RAW, WAR and WAW pair."""
+        W = self.warps
+        val_op = {op.out.id: op for op in self.ops if op.out is not None}
+        vc = {}  # op id -> vector clock after completion
+        last_vc = [[0] * W for _ in range(W)]
+        for i in self.order:
+            op = self.ops[i]
+            c = list(last_vc[op.warp])
+            for w2, need in enumerate(self.waits[i]):
+                if need:
+                    other = self.streams[w2][need - 1]
+                    assert other in vc, "wait on a record later in the linear order (deadlock)"
+                    c = [max(a, b) for a, b in zip(c, vc[other])]
+            # every requirement must be implied by the clock BEFORE executing
+            for w2, need in enumerate(self.full_reqs[i]):
+                assert c[w2] >= need, f"op {i}: missing ordering on warp {w2}"
+            c[op.warp] = op.sidx + 1
+            vc[i] = c
+            last_vc[op.warp] = c
+        # slot exclusivity along L
+        holder = {}
+        for i in self.order:
+            op = self.ops[i]
+            if op.out is not None:
+                holder[self.slot_of[op.out.id]] = op.out.id
+            for v in op.src_vals():
+                assert holder.get(self.slot_of[v.id]) == v.id, "operand slot overwritten before use"
+
     def _enc_operand(self, o: Operand) -> int:
         if o.flags & F_GLOBAL:
             buf, fld = o.gl
@@ -584,43 +654,50 @@ class Builder:
 
         a = idx(o.a)
         b = idx(o.b) if o.b is not None else 0
-        return a | (b << 8) | ((o.ca & 0xF) << 16) | ((o.cb & 0xF) << 20) | (o.flags << 24)
+        flags = o.flags
+        if flags == 0 and o.ca == 1 and (o.b is None or o.cb == 0) and a < self.nslots:
+            flags |= F_SIMPLE
+        return a | (b << 8) | ((o.ca & 0xF) << 16) | ((o.cb & 0xF) << 20) | (flags << 24)
 
     def encode(self):
-        """Returns (prog: bytes [W][nrec][32 words], nrec)."""
+        """Returns (prog: bytes [W][nrec][32 words], nrec).  Words 27, 29, 30, 31 hold eight 16-bit progress
+        requirements (warps 0..7)."""
         W = self.warps
-        streams = [[] for _ in range(W)]
-        for s, st in enumerate(self.steps):
-            for w in range(W):
-                recs = []
-                for i in st[w]:
-                    op = self.ops[i]
-                    words = [0] * REC_WORDS
-                    dst = 0 if op.dst_global is not None else self.slot_of[op.out.id]
-                    hdr = OP_MAC | (dst << 8) | (len(op.terms) << 16) | (len(op.epi) << 20) | (op.ncorr << 22)
-                    aux = op.xmask << 16
-                    if op.dst_global is not None:
-                        hdr |= H_DSTG
-                        aux |= op.dst_global[0] | (op.dst_global[1] << 8)
-                        if op.per_batch:
-                            hdr |= H_DSTBATCH
-                    if op.pad_const is not None:
-                        hdr |= H_PADCONST
-                        aux |= op.pad_const.cidx << 24
-                    words[0], words[1] = hdr, aux
-                    for t, (x, y) in enumerate(op.terms):
-                        words[2 + 2 * t] = self._enc_operand(x)
-                        words[3 + 2 * t] = self._enc_operand(y)
-                    for e, z in enumerate(op.epi):
-                        words[26 + 2 * e] = self._enc_operand(z)
-                    recs.append(words)
-                if not recs:
-                    recs.append([OP_NOP] + [0] * (REC_WORDS - 1))
-                if s > 0:
-                    recs[0][0] |= H_BAR
-                streams[w] += recs
-        nrec = max(len(s) for s in streams)
-        # pad with NOPs WITHOUT barrier flags (all barriers already matched per step)
+        assert W <= 8
+        streams = []
+        for w in range(W):
+            recs = []
+            for i in self.streams[w]:
+                op = self.ops[i]
+                words = [0] * REC_WORDS
+                dst = 0 if op.dst_global is not None else self.slot_of[op.out.id]
+                hdr = OP_MAC | (dst << 8) | (len(op.terms) << 16) | (len(op.epi) << 20) | (op.ncorr << 22)
+                aux = op.xmask << 16
+                if op.dst_global is not None:
+                    hdr |= H_DSTG
+                    aux |= op.dst_global[0] | (op.dst_global[1] << 8)
+                    if op.per_batch:
+                        hdr |= H_DSTBATCH
+                if op.pad_const is not None:
+                    hdr |= H_PADCONST
+                    aux |= op.pad_const.cidx << 24
+                words[0], words[1] = hdr, aux
+                for t, (x, y) in enumerate(op.terms):
+                    words[2 + 2 * t] = self._enc_operand(x)
+                    words[3 + 2 * t] = self._enc_operand(y)
+                for e, z in enumerate(op.epi):
+                    words[26 + 2 * e] = self._enc_operand(z)
+                wt = self.waits[i] + [0] * (8 - W)
+                assert max(wt) < 65536
+                if any(wt):
+                    words[0] |= H_BAR  # "has waits"
+                words[27] = wt[0] | (wt[1] << 16)
+                words[29] = wt[2] | (wt[3] << 16)
+                words[30] = wt[4] | (wt[5] << 16)
+                words[31] = wt[6] | (wt[7] << 16)
+                recs.append(words)
+            streams.append(recs)
+        nrec = max(len(s_) for s_ in streams)
         blob = bytearray()
         for w in range(W):
             recs = streams[w] + [[OP_NOP] + [0] * (REC_WORDS - 1)] * (nrec - len(streams[w]))
@@ -634,17 +711,3 @@ class Builder:
             out += struct.pack("<12I", *[(c >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
         return bytes(out)
 
-    def check_hazards(self):
-        """No slot is read and written (or written twice) inside one step."""
-        for s, st in enumerate(self.steps):
-            reads, writes = set(), set()
-            for wl in st:
-                for i in wl:
-                    op = self.ops[i]
-                    for v in op.src_vals():
-                        reads.add(self.slot_of[v.id])
-                    if op.out is not None:
-                        sl = self.slot_of[op.out.id]
-                        assert sl not in writes, f"WAW hazard in step {s}"
-                        writes.add(sl)
-            assert not (reads & writes), f"RAW/WAR hazard in step {s}: {reads & writes}"

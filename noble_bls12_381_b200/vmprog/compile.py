@@ -13,7 +13,7 @@ from . import tower
 
 MAGIC = 0x4D563242  # 'B2VM'
 VERSION = 1
-DEFAULT_WARPS = 6
+DEFAULT_WARPS = 8
 DEFAULT_SLOTS = 72
 
 

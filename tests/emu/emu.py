@@ -21,7 +21,7 @@ def lib():
     return _LIB
 
 
-def run_program(b, buffers, n_items, nslots=72):
+def run_program(b, buffers, n_items, nslots=72, policy=2):
     """b: scheduled+allocated Builder.  buffers: {buf_id: (bytearray, stride)} (outputs written in place)."""
     prog, nrec = b.encode()
     consts = b.const_table()
@@ -35,6 +35,6 @@ def run_program(b, buffers, n_items, nslots=72):
         bases[i] = ctypes.addressof(arr)
         strides[i] = stride
     rc = lib().vm_emu_run(prog, b.warps, nrec, consts, len(b.consts), b.nslots, b.nfar, n_items,
-                          ctypes.cast(bases, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8))), strides, nbuf)
+                          ctypes.cast(bases, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8))), strides, nbuf, policy)
     assert rc == 0, rc
     return buffers

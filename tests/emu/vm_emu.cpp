@@ -25,48 +25,55 @@ void emu_mac_redc(int n, const uint32_t* a, const uint32_t* b, int rounds, uint3
 void emu_add_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::add_mod(r, a, b); }
 void emu_sub_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::sub_mod(r, a, b); }
 
-// Runs a program on n_items items.  bufs: base pointers (host memory), strides in bytes.
+// Runs a program on n_items items with the dataflow semantics of the kernel: a warp may execute its next
+// record only when the progress counters it names are reached.  `policy` picks which runnable warp goes next
+// (0 round-robin, 1 highest index first, 2 pseudo-random) so that missing waits show up as wrong results.
 int vm_emu_run(const uint32_t* prog, int warps, int nrec, const uint32_t* consts, int nconst, int nslots,
-               int nfar, int n_items, uint8_t** bases, const uint32_t* strides, int nbuf) {
+               int nfar, int n_items, uint8_t** bases, const uint32_t* strides, int nbuf, int policy) {
     vm::Buffer buf[vm::kMaxBuffers];
     memset(buf, 0, sizeof(buf));
     for (int i = 0; i < nbuf && i < vm::kMaxBuffers; ++i) { buf[i].base = bases[i]; buf[i].stride = strides[i]; }
     std::vector<uint32_t> slots((size_t)nslots * vm::kSlotWords), far((size_t)(nfar ? nfar : 1) * vm::kSlotWords);
     int nbatch = (n_items + 31) / 32;
+    uint32_t rng = 12345;
     for (int batch = 0; batch < nbatch; ++batch) {
-        std::vector<int> pc(warps, 0);
-        std::vector<bool> passed(warps, false);  // barrier of record pc[w] already passed
+        std::vector<uint32_t> pc(warps, 0);
         for (;;) {
-            bool progress = false, all_done = true;
+            std::vector<int> runnable;
+            bool all_done = true;
             for (int w = 0; w < warps; ++w) {
-                while (pc[w] < nrec) {
-                    const uint32_t* rec = prog + ((size_t)w * nrec + pc[w]) * vm::kRecWords;
-                    if ((rec[0] & vm::H_BAR) && !passed[w]) break;  // wait at barrier
-                    for (uint32_t lane = 0; lane < 32; ++lane) {
-                        vm::Ctx c;
-                        c.slots = slots.data(); c.consts = consts; c.far = far.data(); c.nslots = nslots;
-                        c.lane = lane;
-                        uint32_t item = batch * 32 + lane;
-                        c.store_ok = item < (uint32_t)n_items;
-                        c.item = c.store_ok ? item : (uint32_t)n_items - 1;
-                        c.buf = buf;
-                        c.batch = batch;
-                        vm::exec_record(c, rec[0], rec[1], [&](uint32_t i) { return rec[i]; });
+                if (pc[w] >= (uint32_t)nrec) continue;
+                all_done = false;
+                const uint32_t* rec = prog + ((size_t)w * nrec + pc[w]) * vm::kRecWords;
+                bool ok = true;
+                if (rec[0] & vm::H_BAR) {
+                    const uint32_t ww[4] = {rec[27], rec[29], rec[30], rec[31]};
+                    for (int k = 0; k < 8 && k < warps; ++k) {
+                        uint32_t need = (ww[k / 2] >> (16 * (k & 1))) & 0xFFFF;
+                        if (pc[k] < need) ok = false;
                     }
-                    passed[w] = false;
-                    ++pc[w];
-                    progress = true;
                 }
-                if (pc[w] < nrec) all_done = false;
+                if (ok) runnable.push_back(w);
             }
             if (all_done) break;
-            // every unfinished warp now waits at a barrier: release them together
-            bool all_at_bar = true;
-            for (int w = 0; w < warps; ++w)
-                if (pc[w] >= nrec) { all_at_bar = false; }  // a finished warp can't arrive: program bug
-            if (!all_at_bar) { fprintf(stderr, "vm_emu: barrier count mismatch between warps\n"); return -2; }
-            for (int w = 0; w < warps; ++w) passed[w] = true;
-            (void)progress;
+            if (runnable.empty()) { fprintf(stderr, "vm_emu: deadlock\n"); return -2; }
+            int w;
+            if (policy == 0) w = runnable[0];
+            else if (policy == 1) w = runnable.back();
+            else { rng = rng * 1664525u + 1013904223u; w = runnable[(rng >> 16) % runnable.size()]; }
+            const uint32_t* rec = prog + ((size_t)w * nrec + pc[w]) * vm::kRecWords;
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                vm::Ctx c;
+                c.slots = slots.data(); c.consts = consts; c.far = far.data(); c.nslots = nslots;
+                c.lane = lane;
+                uint32_t item = batch * 32 + lane;
+                c.store_ok = item < (uint32_t)n_items;
+                c.item = c.store_ok ? item : (uint32_t)n_items - 1;
+                c.buf = buf;
+                c.batch = batch;
+                vm::exec_record(c, rec[0], rec[1], [&](uint32_t i) { return rec[i]; });
+            }
+            ++pc[w];
         }
     }
     return 0;
