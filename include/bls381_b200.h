@@ -80,6 +80,25 @@ int bls381_miller_product(const uint8_t* g1, const uint8_t* g2, size_t n, int wi
 int bls381_miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int with_final_exp,
                               uint8_t* d_out_fp12, void* cuda_stream);
 
+/* PointG1.fromHex for 48-byte compressed public keys incl. assertValidity     replaces index.ts:298-327, 383-388
+ *   out96: affine x || y; status[i]: OK / INFINITY (flag bit set, the reference returns ZERO) /
+ *   BAD_ENCODING ('Invalid compressed G1 point') / NOT_IN_SUBGROUP.                                  */
+int bls381_g1_decompress_batch(const uint8_t* in48, size_t n, uint8_t* out96, int32_t* status);
+/* PointG2.fromSignature for 96-byte compressed signatures incl. assertValidity  replaces index.ts:500-530, 633-638
+ *   out192: affine x.c0 || x.c1 || y.c0 || y.c1; status: OK / INFINITY / NO_SQRT / NOT_IN_SUBGROUP       */
+int bls381_g2_decompress_batch(const uint8_t* in96, size_t n, uint8_t* out192, int32_t* status);
+/* PointG2.hashToCurve(msg, {DST})                                              replaces index.ts:481-490
+ * (expand_message_xmd index.ts:207-231, hash_to_field :240-267, SWU math.ts:1220-1267, 3-isogeny
+ *  math.ts:1315-1325, clearCofactor index.ts:659-672).  msgs: packed bytes, msg_off[n+1] byte offsets.
+ *   out192: affine H(m_i).                                                                             */
+int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst,
+                            size_t dst_len, uint8_t* out192);
+/* verifyBatch(signature, messages, publicKeys) for byte inputs                  replaces index.ts:792-821
+ *   sig96: aggregated signature; pks48: n compressed public keys; status: n + 1 codes (public keys, then signature).
+ *   *verdict: 1 true, 0 false, -1 = the reference would throw (a decoding / validity error, see status).   */
+int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
+                        size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status);
+
 /* Generic tower-VM launch (used by the tests and by the entry points above).
  *   program  : name of a loaded program ("pairing", "miller", "final_exp", ...)
  *   bufs     : up to 8 DEVICE buffers; strides[i] = bytes per item in buffer i                      */

@@ -34,6 +34,10 @@ def _load():
     lib.bls381_vm_run_dev.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_vm_load.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
     lib.bls381_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    lib.bls381_g1_decompress_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_g2_decompress_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_hash_to_g2_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_verify_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     return lib
 
 
@@ -42,6 +46,7 @@ EXPORTS = [
     "bls381_pairing_batch", "bls381_pairing_batch_dev", "bls381_final_exp_batch", "bls381_final_exp_batch_dev",
     "bls381_miller_product", "bls381_miller_product_dev", "bls381_vm_run_dev", "bls381_vm_load",
     "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms",
+    "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
 ]
 
 
@@ -75,6 +80,41 @@ class Engine:
         out = ctypes.create_string_buffer(576)
         self._check(self.lib.bls381_miller_product(g1, g2, n, int(with_final_exp), out))
         return out.raw
+
+    # ---- ingest / verification ---------------------------------------------------------------------
+    @staticmethod
+    def _pack(msgs):
+        off = [0]
+        for m in msgs:
+            off.append(off[-1] + len(m))
+        return b"".join(msgs), (ctypes.c_uint64 * len(off))(*off)
+
+    def g1_decompress_batch(self, keys48: bytes, n: int):
+        out = ctypes.create_string_buffer(96 * n)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g1_decompress_batch(keys48, n, out, st))
+        return out.raw, list(st)
+
+    def g2_decompress_batch(self, sigs96: bytes, n: int):
+        out = ctypes.create_string_buffer(192 * n)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g2_decompress_batch(sigs96, n, out, st))
+        return out.raw, list(st)
+
+    def hash_to_g2_batch(self, msgs, dst: bytes) -> bytes:
+        packed, off = self._pack(msgs)
+        out = ctypes.create_string_buffer(192 * len(msgs))
+        self._check(self.lib.bls381_hash_to_g2_batch(packed, off, len(msgs), dst, len(dst), out))
+        return out.raw
+
+    def verify_batch(self, sig96: bytes, msgs, pks48: bytes, dst: bytes):
+        """-> (verdict in {1, 0, -1}, status list of n + 1 codes)"""
+        n = len(msgs)
+        packed, off = self._pack(msgs)
+        v = ctypes.c_int(0)
+        st = (ctypes.c_int32 * (n + 1))()
+        self._check(self.lib.bls381_verify_batch(sig96, packed, off, pks48, n, dst, len(dst), ctypes.byref(v), st))
+        return v.value, list(st)
 
     # ---- device-pointer entry points (ints = CUDA device addresses, e.g. torch tensor.data_ptr()) ----
     def pairing_batch_dev(self, d_g1: int, d_g2: int, n: int, with_final_exp: bool, d_out: int, stream: int = 0):

@@ -15,6 +15,7 @@
 
 #include "../../include/bls381_b200.h"
 #include "vm_kernel.cu"  // single translation unit: the interpreter kernel
+#include "sha256_xmd.cuh"
 
 namespace {
 
@@ -32,8 +33,9 @@ struct State {
     uint32_t* d_far = nullptr;
     size_t far_bytes = 0;
     // grow-only device staging for the host entry points
-    uint8_t* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t stage_bytes[4] = {0, 0, 0, 0};
+    static constexpr int kStages = 10;
+    uint8_t* d_stage[kStages] = {};
+    size_t stage_bytes[kStages] = {};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
@@ -69,7 +71,7 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6];
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
-    if (p.warps != 6 && p.warps != 8) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
@@ -127,7 +129,8 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     if (rc) return rc;
     const uint32_t nbatch = (uint32_t)((n + 31) / 32);
     const size_t smem_est = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 1024;
-    int ctas_per_sm = std::max(1, std::min(p->warps == 6 ? 3 : 2, (int)(232448 / smem_est)));
+    const int max_ctas = p->warps == 2 ? 8 : (p->warps == 4 ? 4 : 2);
+    int ctas_per_sm = std::max(1, std::min(max_ctas, (int)(232448 / smem_est)));
     if (g.force_ctas > 0) ctas_per_sm = std::min(ctas_per_sm, g.force_ctas);
     const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)(g.sm_count * ctas_per_sm));
     const size_t far_need = (size_t)grid * std::max<uint32_t>(p->nfar, 1) * vm::kSlotWords * 4;
@@ -154,7 +157,9 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     }
     const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64;  // slots + constants + progress counters
     g.launches.fetch_add(1);
-    if (p->warps == 6) return ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
+    if (p->warps == 2) return launch_w<2, 8>(L, grid, smem, s);
+    if (p->warps == 4) return launch_w<4, 4>(L, grid, smem, s);
+    if (p->warps == 6) return launch_w<6, 2>(L, grid, smem, s);
     if (p->warps == 8) return launch_w<8, 2>(L, grid, smem, s);
     return fail(BLS381_EPROGRAM, "unsupported warp count");
 }
@@ -206,6 +211,55 @@ int miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int f
     CUDA_TRY(cudaMemcpyAsync(d_out, res, 576, cudaMemcpyDeviceToDevice, s));
     return BLS381_OK;
 }
+
+// ---- ingest: decompression, hash-to-curve, verifyBatch ------------------------------------------------
+__global__ void xmd_kernel(const uint8_t* msgs, const uint64_t* off, size_t n, const uint8_t* dst_prime,
+                           uint32_t dst_prime_len, uint8_t* out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sha::expand_xmd_256(msgs + off[i], off[i + 1] - off[i], dst_prime, dst_prime_len, out + 256 * i);
+}
+
+// DST' = DST || len(DST)  (oversize DSTs are hashed first, index.ts:214)
+int make_dst_prime(const uint8_t* dst, size_t dst_len, std::vector<uint8_t>& out) {
+    out.clear();
+    if (dst_len > 255) {
+        sha::Ctx c;
+        sha::init(c);
+        const char* pre = "H2C-OVERSIZE-DST-";
+        sha::update(c, reinterpret_cast<const uint8_t*>(pre), 17);
+        sha::update(c, dst, dst_len);
+        out.resize(32);
+        sha::final(c, out.data());
+    } else {
+        out.assign(dst, dst + dst_len);
+    }
+    out.push_back((uint8_t)out.size());
+    return BLS381_OK;
+}
+
+int run3(const char* prog, uint8_t* in, uint32_t in_stride, uint8_t* out, uint32_t out_stride, int32_t* d_status,
+         size_t n, cudaStream_t s) {
+    uint8_t* bufs[6] = {in, nullptr, out, nullptr, nullptr, reinterpret_cast<uint8_t*>(d_status)};
+    uint32_t strides[6] = {in_stride, 0, out_stride, 0, 0, 4};
+    return vm_run(prog, bufs, strides, 6, n, s);
+}
+
+// msgs (device, packed) -> n x 192 B affine H(m) at d_out
+int hash_to_g2_dev(const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const uint8_t* dst, size_t dst_len,
+                   uint8_t* d_out, cudaStream_t s) {
+    std::vector<uint8_t> dp;
+    make_dst_prime(dst, dst_len, dp);
+    int rc;
+    if ((rc = stage(4, n * 256)) || (rc = stage(5, 512))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[5], dp.data(), dp.size(), cudaMemcpyHostToDevice, s));
+    xmd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_msgs, d_off, n, g.d_stage[5], (uint32_t)dp.size(), g.d_stage[4]);
+    CUDA_TRY(cudaGetLastError());
+    return run3("hash_to_g2", g.d_stage[4], 256, d_out, 192, nullptr, n, s);
+}
+
+const uint8_t kNegG1[96] = {  // -G1_BASE affine (x, p - y)
+    0x17, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f, 0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58, 0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb, 0x11, 0x4d, 0x1d, 0x68, 0x55, 0xd5, 0x45, 0xa8, 0xaa, 0x7d, 0x76, 0xc8, 0xcf, 0x2e, 0x21, 0xf2, 0x67, 0x81, 0x6a, 0xef, 0x1d, 0xb5, 0x07, 0xc9, 0x66, 0x55, 0xb9, 0xd5, 0xca, 0xac, 0x42, 0x36, 0x4e, 0x6f, 0x38, 0xba, 0x0e, 0xcb, 0x75, 0x1b, 0xad, 0x54, 0xdc, 0xd6, 0xb9, 0x39, 0xc2, 0xca};
 
 // ---- IMAD.WIDE issue-rate microbenchmark -------------------------------------------------------
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters) {
@@ -278,7 +332,7 @@ int bls381_shutdown(void) {
     if (g.d_far) cudaFree(g.d_far);
     g.d_far = nullptr;
     g.far_bytes = 0;
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < State::kStages; ++k) {
         if (g.d_stage[k]) cudaFree(g.d_stage[k]);
         g.d_stage[k] = nullptr;
         g.stage_bytes[k] = 0;
@@ -396,6 +450,105 @@ int bls381_miller_product(const uint8_t* g1, const uint8_t* g2, size_t n, int wi
     float ms = 0;
     cudaEventElapsedTime(&ms, g.ev0, g.ev1);
     g.last_ms = ms;
+    return BLS381_OK;
+}
+
+int bls381_g1_decompress_batch(const uint8_t* in48, size_t n, uint8_t* out96, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in48 || !out96 || !status) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    if ((rc = stage(0, n * 48)) || (rc = stage(2, n * 96)) || (rc = stage(6, n * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in48, n * 48, cudaMemcpyHostToDevice, g.stream));
+    if ((rc = run3("g1_decompress", g.d_stage[0], 48, g.d_stage[2], 96, (int32_t*)g.d_stage[6], n, g.stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out96, g.d_stage[2], n * 96, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return BLS381_OK;
+}
+
+int bls381_g2_decompress_batch(const uint8_t* in96, size_t n, uint8_t* out192, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in96 || !out192 || !status) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    if ((rc = stage(0, n * 96)) || (rc = stage(2, n * 192)) || (rc = stage(6, n * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in96, n * 96, cudaMemcpyHostToDevice, g.stream));
+    if ((rc = run3("g2_decompress", g.d_stage[0], 96, g.d_stage[2], 192, (int32_t*)g.d_stage[6], n, g.stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return BLS381_OK;
+}
+
+int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst, size_t dst_len,
+                            uint8_t* out192) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!msg_off || !dst || !out192 || (!msgs && msg_off[n] != 0)) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    const size_t mbytes = msg_off[n];
+    if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(2, n * 192))) return rc;
+    if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, g.stream));
+    if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, g.d_stage[2], g.stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return BLS381_OK;
+}
+
+int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
+                        size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!sig96 || !msg_off || !pks48 || !dst || !verdict || !status) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return fail(BLS381_EINVAL, "Expected non-empty messages array");
+    int rc;
+    const size_t mbytes = msg_off[n];
+    // staging: 0 msgs, 1 offsets, 7 pks(48) + sig(96), 8 g1 pairs (n+1) x 96, 9 g2 pairs (n+1) x 192, 6 status (n+1)
+    if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(7, n * 48 + 96)) ||
+        (rc = stage(8, (n + 1) * 96 + 576)) || (rc = stage(9, (n + 1) * 192)) || (rc = stage(6, (n + 1) * 4)))
+        return rc;
+    cudaStream_t s = g.stream;
+    if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], pks48, n * 48, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[7] + n * 48, sig96, 96, cudaMemcpyHostToDevice, s));
+    uint8_t* d_g1 = g.d_stage[8] + 576;  // first 576 B: result
+    uint8_t* d_g2 = g.d_stage[9];
+    int32_t* d_st = (int32_t*)g.d_stage[6];
+    CUDA_TRY(cudaEventRecord(g.ev0, s));
+    // publicKeys.map(normP1)  (index.ts:801)
+    if ((rc = run3("g1_decompress", g.d_stage[7], 48, d_g1, 96, d_st, n, s))) return rc;
+    // normP2(signature)  (index.ts:799)
+    if ((rc = run3("g2_decompress", g.d_stage[7] + n * 48, 96, d_g2 + n * 192, 192, d_st + n, 1, s))) return rc;
+    // messages.map(normP2Hash)  (index.ts:800)
+    if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, d_g2, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_g1 + n * 96, kNegG1, 96, cudaMemcpyHostToDevice, s));
+    // product of the n + 1 Miller loops and one final exponentiation (index.ts:812-816)
+    if ((rc = miller_product_dev(d_g1, d_g2, n + 1, 1, g.d_stage[8], s))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, s));
+    uint8_t res[576];
+    CUDA_TRY(cudaMemcpyAsync(res, g.d_stage[8], 576, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, d_st, (n + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    bool one = res[47] == 1;
+    for (int i = 0; i < 576 && one; ++i)
+        if (i != 47 && res[i] != 0) one = false;
+    // reference semantics: decoding errors throw (reported as verdict -1 + status codes); an infinity public key
+    // or signature makes pairing() throw inside the try block => false (index.ts:716, 818-820)
+    int v = one ? 1 : 0;
+    for (size_t i = 0; i <= n; ++i) {
+        if (status[i] == BLS381_ST_INFINITY) { if (v > 0) v = 0; }
+        else if (status[i] != BLS381_ST_OK) v = -1;
+    }
+    *verdict = v;
     return BLS381_OK;
 }
 

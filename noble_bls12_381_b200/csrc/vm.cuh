@@ -35,7 +35,11 @@ static constexpr int kConstSlots = 64;
 // ---- record layout -------------------------------------------------------------------------------
 // word 0 (header): [7:0] opcode  [15:8] dst  [19:16] T  [21:20] E  [24:22] ncorr  [25] has_waits
 //                  [26] dst_global  [27] reserved  [28] dst_batch (lane 0 stores at item/32)
-//                  [29] pad_const (padding lanes yield constant aux[31:24])
+//                  [29] pad_const (padding lanes yield constant aux[31:24])  [27] dst_word (int32 store)
+//                  [30] post_iszero  [31] post_gt_half  (turn the canonical result into a 0/1 flag)
+// opcode OP_SEL  : dst = flag ? A : B  (word 2 = flag operand, word 3 = A operand, word 4 = B operand)
+// opcode OP_BIT  : dst = bit `word 3` (0 = least significant) of the big-endian field of `word 4` bytes at
+//                  the GLOBAL operand in word 2
 // word 1 (aux)   : [7:0] dst buffer id  [15:8] dst field   [23:16] lane xor mask (for XLANE terms)
 //                  [31:24] constant index for pad_const
 // words 2..25    : T terms, 2 words each:
@@ -45,16 +49,19 @@ static constexpr int kConstSlots = 64;
 // words 27,29,30,31: eight 16-bit progress requirements (warp 0..7): this record may start only when
 //                  warp w has completed at least that many records of its stream (0 = no requirement)
 // operand flags  : bit0 CONST  (A/B index the constant table instead of slots)
-//                  bit1 GLOBAL (A = buffer id, B = field index: wire-format big-endian 48-byte field)
+//                  bit1 GLOBAL (A = buffer id, B = byte offset/16 of a big-endian field; cA = number of top
+//                       bits to clear (compression flags), cB = 0: 48-byte field, 1: 32-byte field)
 //                  bit2 XLANE  (read the slot column of lane ^ mask)
 //                  bit3 SIMPLE (operand is exactly one shared-memory slot, coefficient +1: fast path)
-enum : uint32_t { OP_NOP = 0, OP_MAC = 1 };
+enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3 };
 enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8 };
 static constexpr uint32_t H_BAR = 1u << 25;
 static constexpr uint32_t H_DSTG = 1u << 26;
-static constexpr uint32_t H_DSTRAW = 1u << 27;
 static constexpr uint32_t H_DSTBATCH = 1u << 28;  // global store by lane 0 only, at index item/32
 static constexpr uint32_t H_PADCONST = 1u << 29;  // lanes beyond n_items produce constant aux[31:24] instead
+static constexpr uint32_t H_POST_ISZERO = 1u << 30;  // result := (result == 0) ? 1 : 0   (plain integer flag)
+static constexpr uint32_t H_POST_GTHALF = 1u << 31;  // result := (result > (p-1)/2) ? 1 : 0
+static constexpr uint32_t H_DSTWORD = 1u << 27;      // global store of the low 32 bits as int32 (status arrays)
 
 struct Buffer {
     uint8_t* base;      // device pointer
@@ -137,19 +144,28 @@ FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
 #endif
 }
 
-// wire format: 48-byte big-endian field element -> 12 little-endian limbs
-FPC_DEV void load_wire(uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field) {
+// wire format: big-endian field (48 or 32 bytes) at byte offset 16*off16 -> 12 little-endian limbs
+FPC_DEV void load_wire(uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t off16, uint32_t clear_top, uint32_t short32) {
     const Buffer& b = c.buf[bufid];
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(b.base + (size_t)c.item * b.stride + field * 48u);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(b.base + (size_t)c.item * b.stride + off16 * 16u);
+    if (short32) {
 #pragma unroll
-    for (int k = 0; k < 12; ++k) r[k] = bswap32(p[11 - k]);
+        for (int k = 0; k < 8; ++k) r[k] = bswap32(p[7 - k]);
+#pragma unroll
+        for (int k = 8; k < 12; ++k) r[k] = 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = bswap32(p[11 - k]);
+        r[11] &= 0xFFFFFFFFu >> clear_top;
+    }
 }
 
-FPC_DEV void store_wire(const uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t field, bool per_batch) {
+FPC_DEV void store_wire(const uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t off16, bool per_batch, bool word) {
     if (per_batch ? (c.lane != 0) : !c.store_ok) return;
     const Buffer& b = c.buf[bufid];
     const size_t idx = per_batch ? (size_t)(c.batch) : (size_t)c.item;
-    uint32_t* p = reinterpret_cast<uint32_t*>(b.base + idx * b.stride + field * 48u);
+    uint32_t* p = reinterpret_cast<uint32_t*>(b.base + idx * b.stride + off16 * 16u);
+    if (word) { p[0] = r[0]; return; }
 #pragma unroll
     for (int k = 0; k < 12; ++k) p[11 - k] = bswap32(r[k]);
 }
@@ -199,7 +215,7 @@ FPC_DEV void load_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask)
     const uint32_t a = w & 0xFF, b = (w >> 8) & 0xFF, flags = w >> 24;
     const int ca = sext4(w >> 16), cb = sext4(w >> 20);
     if (flags & F_GLOBAL) {
-        load_wire(r, c, a, b);
+        load_wire(r, c, a, b, (w >> 16) & 0xF, (w >> 20) & 0xF);
         return;
     }
     load_one(r, c, a, flags, xmask);
@@ -226,7 +242,24 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
     const uint32_t xmask = (aux >> 16) & 0xFF;
 
     uint32_t r[12];
-    if (T > 0) {
+    if (op == OP_SEL) {
+        uint32_t f[12], b2[12];
+        load_operand(f, c, W(2), xmask);
+        load_operand(r, c, W(3), xmask);
+        load_operand(b2, c, W(4), xmask);
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) any |= f[k];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = any ? r[k] : b2[k];
+    } else if (op == OP_BIT) {
+        const uint32_t w2 = W(2), bit = W(3), nbytes = W(4);
+        const Buffer& bf = c.buf[w2 & 0xFF];
+        const uint8_t* p = bf.base + (size_t)c.item * bf.stride + ((w2 >> 8) & 0xFF) * 16u;
+        const uint32_t byte = p[nbytes - 1 - (bit >> 3)];
+        fpc::zero12(r);
+        r[0] = (byte >> (bit & 7)) & 1u;
+    } else if (T > 0) {
         fpc::Acc A;
         fpc::acc_zero(A);
         for (uint32_t t = 0; t < T; ++t) {
@@ -245,13 +278,29 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
         (void)fpc::add12(r, r, z);
     }
     fpc::correct(r, ncorr);
+    if (hdr & (H_POST_ISZERO | H_POST_GTHALF)) {
+        uint32_t flag;
+        if ((hdr & H_POST_ISZERO) && (hdr & H_POST_GTHALF)) {
+            flag = r[0] & 1u;  // parity (sgn0)
+        } else if (hdr & H_POST_ISZERO) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) any |= r[k];
+            flag = any ? 0u : 1u;
+        } else {
+            uint32_t t[12];
+            flag = fpc::sub12(t, fpc::kHalfP, r);  // borrow <=> r > (p-1)/2
+        }
+        fpc::zero12(r);
+        r[0] = flag;
+    }
     if ((hdr & H_PADCONST) && !c.store_ok) {
         const uint32_t* s = c.consts + (aux >> 24) * 12;
 #pragma unroll
         for (int k = 0; k < 12; ++k) r[k] = s[k];
     }
     if (hdr & H_DSTG) {
-        store_wire(r, c, aux & 0xFF, (aux >> 8) & 0xFF, (hdr & H_DSTBATCH) != 0);
+        store_wire(r, c, aux & 0xFF, (aux >> 8) & 0xFF, (hdr & H_DSTBATCH) != 0, (hdr & H_DSTWORD) != 0);
     } else {
         store_slot(r, c, dst);
     }

@@ -27,9 +27,9 @@ R_MOD_P = R % P
 R2_MOD_P = R * R % P
 P_OVER_R = P / R  # ~0.1016
 
-OP_NOP, OP_MAC = 0, 1
+OP_NOP, OP_MAC, OP_SEL, OP_BIT = 0, 1, 2, 3
 F_CONST, F_GLOBAL, F_XLANE, F_SIMPLE = 1, 2, 4, 8
-H_BAR, H_DSTG, H_DSTBATCH, H_PADCONST = 1 << 25, 1 << 26, 1 << 28, 1 << 29
+H_BAR, H_DSTG, H_DSTWORD, H_DSTBATCH, H_PADCONST, H_POST_ISZERO, H_POST_GTHALF = 1 << 25, 1 << 26, 1 << 27, 1 << 28, 1 << 29, 1 << 30, 1 << 31
 REC_WORDS = 32
 MAX_TERMS = 12
 MAX_SUM_BOUND = 80.0  # sum of |x|*|y| bounds in units of p^2 that fits the 768-bit accumulator
@@ -157,7 +157,9 @@ class Operand:
 
     def bound(self):
         if self.flags & F_GLOBAL:
-            return R / P  # any 384-bit value
+            if self.gl[3]:
+                return (1 << 256) / P  # 32-byte field
+            return (1 << (384 - self.gl[2])) / P  # any (384 - cleared)-bit value
         return abs(self.ca) + abs(self.cb)
 
 
@@ -170,6 +172,11 @@ class Op:
     out: Val | None = None
     dst_global: tuple | None = None  # (buf, field)
     xmask: int = 0
+    kind: str = "mac"  # mac | sel | bit
+    post: str = ""  # "" | "iszero" | "gthalf"
+    sel: list = field(default_factory=list)  # [flag, a, b] Operands for kind == "sel"
+    bit: tuple | None = None  # (buf, off16, nbytes, bitindex) for kind == "bit"
+    dst_word: bool = False  # int32 status store
     per_batch: bool = False  # global store by lane 0 at index item/32
     pad_const: Val | None = None  # padding lanes (item >= n_items) produce this constant instead
     after: list = field(default_factory=list)  # extra ordering deps (Ops)
@@ -181,6 +188,8 @@ class Op:
     def cost(self):
         """Estimated duration in units of one 12x12 product (calibrated on the ncu instruction counts: a
         product ~300 issued instructions, per-op reduction/correction/decode overhead ~500)."""
+        if self.kind != "mac":
+            return 0.5
         t = len(self.terms)
         return (t + 1.7 if t else 0.6) + 0.1 * len(self.epi)
 
@@ -190,6 +199,8 @@ class Op:
             vs += x.vals() + y.vals()
         for e in self.epi:
             vs += e.vals()
+        for o in self.sel:
+            vs += o.vals()
         return vs
 
 
@@ -236,10 +247,17 @@ class Builder:
         self._after = list(ops)
 
     def inp(self, buf: int, fld: int) -> Val:
-        """Wire-format field `fld` of input buffer `buf` -> Montgomery-form value."""
-        x = Operand(None, 1, flags=F_GLOBAL, gl=(buf, fld))
-        y = Operand(self.R2, 1, flags=F_CONST)
-        # x < 2^384, R2 < p: x*R2/R < 2^384*p/R + p = 2p
+        """Wire-format 48-byte field number `fld` of input buffer `buf` -> Montgomery-form value."""
+        return self.inp_bytes(buf, fld * 48)
+
+    def inp_bytes(self, buf: int, byte_off: int, nbytes: int = 48, clear_top: int = 0, montgomery: bool = True) -> Val:
+        """Big-endian field of 48 or 32 bytes at `byte_off` (multiple of 16); the top `clear_top` bits are
+        masked off (compression flags).  Returns the value mod p in Montgomery form (or the plain integer
+        mod p when montgomery=False)."""
+        assert byte_off % 16 == 0 and nbytes in (48, 32) and 0 <= clear_top <= 15
+        x = Operand(None, 1, flags=F_GLOBAL, gl=(buf, byte_off // 16, clear_top, 1 if nbytes == 32 else 0))
+        y = Operand(self.R2 if montgomery else self.const_raw(R_MOD_P), 1, flags=F_CONST)
+        # x < 2^384, y < p: x*y/R < 2^384*p/R + p = 2p
         return self._new_op([(x, y)], [], 1).out
 
     def out(self, e, buf: int, fld: int, per_batch=False):
@@ -249,9 +267,86 @@ class Builder:
         else:
             x = self._operand(Lin.of(self.mat(e)))
         y = Operand(self.ONE_PLAIN, 1, flags=F_CONST)
-        op = self._new_op([(x, y)], [], 1, dst_global=(buf, fld))
+        op = self._new_op([(x, y)], [], 1, dst_global=(buf, fld * 3))
         op.per_batch = per_batch
         return op
+
+    def out_word(self, flag_val, buf: int, byte_off: int = 0):
+        """Store a plain small integer (flag / status code) as int32 at `byte_off` of the item's record."""
+        assert byte_off % 16 == 0
+        op = self._new_op([], [self._operand(Lin.of(self.mat(flag_val)))], 0, dst_global=(buf, byte_off // 16))
+        op.dst_word = True
+        return op
+
+    # ---- predicates / selection (flags are plain integers 0 / 1 held in slots) -----------------------
+    def is_zero(self, e) -> Val:
+        """1 if the expression is 0 mod p else 0."""
+        v = self.mat_expr_op(e)
+        v.op.post = "iszero"
+        return v
+
+    def gt_half(self, e) -> Val:
+        """1 if the canonical NON-Montgomery value of `e` is > (p-1)/2  (the reference's `(y*2)/P` flag)."""
+        x = self._operand(Lin.of(self.mat(e)))
+        y = Operand(self.ONE_PLAIN, 1, flags=F_CONST)
+        op = self._new_op([(x, y)], [], 1)
+        op.post = "gthalf"
+        return op.out
+
+    def parity(self, e) -> Val:
+        """Least significant bit of the canonical NON-Montgomery value of `e` (sgn0, math.ts:1179-1189)."""
+        x = self._operand(Lin.of(self.mat(e)))
+        y = Operand(self.ONE_PLAIN, 1, flags=F_CONST)
+        op = self._new_op([(x, y)], [], 1)
+        op.post = "parity"
+        return op.out
+
+    def flag_xor(self, f1: Val, f2: Val) -> Val:
+        return self.select(f1, Lin.of(self.flag_not(f2)), Lin.of(f2))
+
+    def mat_expr_op(self, e) -> Val:
+        """Materialise `e` with a FRESH micro-op (so that post-processing flags can be attached)."""
+        e = as_expr(e)
+        if isinstance(e, Lin):
+            e = Quad([], e)
+        n_before = len(self.ops)
+        v = self.mat(e)
+        if v.kind != "op" or v.op.id < n_before or v.op.post:
+            v = self._new_op([], [self._operand(Lin.of(v))], 0).out  # pre-existing value: test a copy
+        return v
+
+    def select(self, flag: Val, a, b) -> Val:
+        """flag ? a : b  (per lane)."""
+        oa = self._operand(self.lin_operand(as_expr(a) if isinstance(as_expr(a), Lin) else Lin.of(self.mat(a))))
+        ob = self._operand(self.lin_operand(as_expr(b) if isinstance(as_expr(b), Lin) else Lin.of(self.mat(b))))
+        of = self._operand(Lin.of(flag))
+        k = max(oa.bound(), ob.bound())
+        ncorr = 0
+        while (1 << ncorr) <= k + 1e-9:
+            ncorr += 1
+        if k <= 1 and oa.ca >= 0 and ob.ca >= 0 and oa.cb >= 0 and ob.cb >= 0:
+            ncorr = 0
+        op = self._new_op([], [], ncorr)
+        op.kind = "sel"
+        op.sel = [of, oa, ob]
+        return op.out
+
+    def bit(self, buf: int, byte_off: int, nbytes: int, bitindex: int) -> Val:
+        """Bit `bitindex` (0 = least significant) of the big-endian `nbytes`-byte field at `byte_off`."""
+        assert byte_off % 16 == 0
+        op = self._new_op([], [], 0)
+        op.kind = "bit"
+        op.bit = (buf, byte_off // 16, nbytes, bitindex)
+        return op.out
+
+    def flag_and(self, f1: Val, f2: Val) -> Val:
+        return self.select(f1, Lin.of(f2), Lin.of(self.const_raw(0)))
+
+    def flag_or(self, f1: Val, f2: Val) -> Val:
+        return self.select(f1, Lin.of(self.const_raw(1)), Lin.of(f2))
+
+    def flag_not(self, f: Val) -> Val:
+        return self.select(f, Lin.of(self.const_raw(0)), Lin.of(self.const_raw(1)))
 
     def pad_select(self, e, const_val: Val) -> Val:
         """Copy of `e` in which padding lanes (items beyond n_items) hold the constant instead."""
@@ -407,7 +502,7 @@ class Builder:
 
         def ev_operand(o: Operand, lane, xmask):
             if o.flags & F_GLOBAL:
-                return inputs[o.gl][lane]
+                return inputs[(o.gl[0], o.gl[1])][lane] & ((1 << (256 if o.gl[3] else 384 - o.gl[2])) - 1)
             ln = lane ^ xmask if (o.flags & F_XLANE) else lane
 
             def one(v):
@@ -421,13 +516,27 @@ class Builder:
         for op in self.ops:
             res = []
             for lane in range(lanes):
-                acc = 0
-                for x, y in op.terms:
-                    acc += ev_operand(x, lane, op.xmask) * ev_operand(y, lane, op.xmask)
-                r = acc * rinv % P if op.terms else 0
-                for e in op.epi:
-                    r += ev_operand(e, lane, op.xmask)
-                res.append(r % P)
+                if op.kind == "sel":
+                    f, a_, b_ = (ev_operand(o, lane, op.xmask) for o in op.sel)
+                    r = a_ if f else b_
+                elif op.kind == "bit":
+                    buf, off16, nbytes, bitindex = op.bit
+                    r = (inputs[(buf, off16)][lane] >> bitindex) & 1
+                else:
+                    acc = 0
+                    for x, y in op.terms:
+                        acc += ev_operand(x, lane, op.xmask) * ev_operand(y, lane, op.xmask)
+                    r = acc * rinv % P if op.terms else 0
+                    for e in op.epi:
+                        r += ev_operand(e, lane, op.xmask)
+                r %= P
+                if op.post == "iszero":
+                    r = 1 if r == 0 else 0
+                elif op.post == "gthalf":
+                    r = 1 if r > (P - 1) // 2 else 0
+                elif op.post == "parity":
+                    r = r & 1
+                res.append(r)
             if op.dst_global is not None:
                 outs[op.dst_global] = res
             else:
@@ -646,8 +755,9 @@ class Builder:
 
     def _enc_operand(self, o: Operand) -> int:
         if o.flags & F_GLOBAL:
-            buf, fld = o.gl
-            return buf | (fld << 8) | (1 << 16) | (F_GLOBAL << 24)
+            buf, off16, clear_top, short32 = o.gl
+            assert off16 < 256
+            return buf | (off16 << 8) | (clear_top << 16) | (short32 << 20) | (F_GLOBAL << 24)
 
         def idx(v):
             return v.cidx if v.kind == "const" else self.slot_of[v.id]
@@ -671,7 +781,16 @@ class Builder:
                 op = self.ops[i]
                 words = [0] * REC_WORDS
                 dst = 0 if op.dst_global is not None else self.slot_of[op.out.id]
-                hdr = OP_MAC | (dst << 8) | (len(op.terms) << 16) | (len(op.epi) << 20) | (op.ncorr << 22)
+                opcode = {"mac": OP_MAC, "sel": OP_SEL, "bit": OP_BIT}[op.kind]
+                hdr = opcode | (dst << 8) | (len(op.terms) << 16) | (len(op.epi) << 20) | (op.ncorr << 22)
+                if op.post == "iszero":
+                    hdr |= H_POST_ISZERO
+                elif op.post == "gthalf":
+                    hdr |= H_POST_GTHALF
+                elif op.post == "parity":
+                    hdr |= H_POST_ISZERO | H_POST_GTHALF
+                if op.dst_word:
+                    hdr |= H_DSTWORD
                 aux = op.xmask << 16
                 if op.dst_global is not None:
                     hdr |= H_DSTG
@@ -687,6 +806,11 @@ class Builder:
                     words[3 + 2 * t] = self._enc_operand(y)
                 for e, z in enumerate(op.epi):
                     words[26 + 2 * e] = self._enc_operand(z)
+                if op.kind == "sel":
+                    words[2], words[3], words[4] = (self._enc_operand(o) for o in op.sel)
+                elif op.kind == "bit":
+                    buf, off16, nbytes, bitindex = op.bit
+                    words[2], words[3], words[4] = buf | (off16 << 8), bitindex, nbytes
                 wt = self.waits[i] + [0] * (8 - W)
                 assert max(wt) < 65536
                 if any(wt):

@@ -9,7 +9,7 @@ import os
 import struct
 import sys
 
-from . import tower
+from . import curves, tower
 
 MAGIC = 0x4D563242  # 'B2VM'
 VERSION = 1
@@ -23,17 +23,25 @@ def image(b) -> bytes:
     return hdr + b.const_table() + prog
 
 
-def compile_program(name: str, warps=DEFAULT_WARPS, nslots=DEFAULT_SLOTS):
-    b = tower.PROGRAMS[name](warps)
+# ingest programs are serial Fp2 chains: fewer warps per CTA, more CTAs per SM
+INGEST_WARPS = {"g1_decompress": 2, "g2_decompress": 4, "hash_to_g2": 4}
+ALL_PROGRAMS = dict(tower.PROGRAMS)
+ALL_PROGRAMS.update(curves.PROGRAMS)
+
+
+def compile_program(name: str, warps=None, nslots=DEFAULT_SLOTS):
+    if warps is None:
+        warps = INGEST_WARPS.get(name, DEFAULT_WARPS)
+    b = ALL_PROGRAMS[name](warps)
     b.schedule()
     b.allocate(nslots)
     b.check_hazards()
     return b
 
 
-def build_all(outdir: str, warps=DEFAULT_WARPS, nslots=DEFAULT_SLOTS, names=None, verbose=True):
+def build_all(outdir: str, warps=None, nslots=DEFAULT_SLOTS, names=None, verbose=True):
     os.makedirs(outdir, exist_ok=True)
-    for name in names or tower.PROGRAMS:
+    for name in names or ALL_PROGRAMS:
         b = compile_program(name, warps, nslots)
         path = os.path.join(outdir, name + ".b2vm")
         with open(path, "wb") as f:

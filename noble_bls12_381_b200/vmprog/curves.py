@@ -1,0 +1,609 @@
+"""G1 / G2 group operations, (de)compression, validity checks and hash-to-curve as tower-VM programs.
+
+Restates (as branch-free dataflow over the 32 lanes of a CTA) the host-side bigint code of the reference:
+  PointG1.fromHex index.ts:298-327, PointG2.fromSignature index.ts:500-530, assertValidity index.ts:383-388 /
+  633-638 (isOnCurve :408-414 / :675-681, isTorsionFree :444-448 / :688-690), psi / psi2 math.ts:1398-1408,
+  clearCofactor index.ts:659-672, map_to_curve_simple_swu_9mod16 math.ts:1220-1267, isogenyMapG2
+  math.ts:1315-1325, ProjectivePoint add/double math.ts:974-1025, multiply math.ts:1061-1078.
+
+Group law: the reference uses the incomplete add-1998-cmo-2 / dbl-1998-cmo-2 formulas plus explicit special
+cases (math.ts:1000-1013).  On the device every point operation uses the COMPLETE projective formulas for
+y^2 = x^3 + b (Renes-Costello-Batina 2015, a = 0), which compute the same group element for every input
+(doubling, inverse, infinity) without branches; all observable results are either affine/compressed bytes or
+projective-equality predicates, so they are bit-identical to the reference's.
+Flags are plain 0/1 integers in slots; `select` picks per lane.
+"""
+from __future__ import annotations
+
+from .builder import Builder, Lin, Quad, Val, P
+from .tower import E2, Tower, X_PARAM, _mat, e2_zero
+
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+# status codes (include/bls381_b200.h)
+ST_OK, ST_INFINITY, ST_NOT_ON_CURVE, ST_NOT_IN_SUBGROUP, ST_BAD_ENCODING, ST_NO_SQRT = 0, 1, 2, 3, 4, 5
+
+
+class FpF:
+    """Field adaptor: Fp elements are Lin/Quad expressions."""
+
+    def __init__(self, t: Tower):
+        self.t, self.b = t, t.b
+
+    def const(self, v):
+        return self.t.fp_const(v)
+
+    def zero(self):
+        return Lin()
+
+    def one(self):
+        return self.t.fp_const(1)
+
+    def mul(self, a, c):
+        return a * c
+
+    def sqr(self, a):
+        return a * a
+
+    def scale(self, a, k):
+        return a * k
+
+    def m(self, a):
+        return _mat(self.b, a)
+
+    def mul_b3(self, a):  # 3*b = 12
+        return self.m(a) * self.t.fp_const(12)
+
+    def mul_b(self, a):  # b = 4 (small scaling)
+        return a * 4
+
+    def is_zero(self, a) -> Val:
+        return self.b.is_zero(a)
+
+    def select(self, f: Val, a, c):
+        return Lin.of(self.b.select(f, self.m(a), self.m(c)))
+
+    def coeffs(self, a):
+        return [a]
+
+
+class Fp2F:
+    """Field adaptor: Fp2 elements are E2."""
+
+    def __init__(self, t: Tower):
+        self.t, self.b = t, t.b
+
+    def const(self, pair):
+        return self.t.e2_const(pair)
+
+    def zero(self):
+        return e2_zero()
+
+    def one(self):
+        return E2(self.t.fp_const(1), Lin())
+
+    def mul(self, a, c):
+        return a * c
+
+    def sqr(self, a):
+        return a.sqr()
+
+    def scale(self, a, k):
+        return a.scale(k)
+
+    def m(self, a):
+        return a.m(self.b)
+
+    def mul_b3(self, a):  # 3*b = 12(1+u)
+        a = a.m(self.b)
+        return a.mul_xi() * self.t.fp_const(12)
+
+    def mul_b(self, a):  # b = 4(1+u)
+        return a.mul_xi().scale(4)
+
+    def is_zero(self, a) -> Val:
+        a = a.m(self.b) if not (isinstance(a.c0, Lin) and isinstance(a.c1, Lin)) else a
+        return self.b.flag_and(self.b.is_zero(a.c0), self.b.is_zero(a.c1))
+
+    def select(self, f: Val, a, c):
+        a, c = a.m(self.b), c.m(self.b)
+        return E2(Lin.of(self.b.select(f, a.c0, c.c0)), Lin.of(self.b.select(f, a.c1, c.c1)))
+
+    def coeffs(self, a):
+        return [a.c0, a.c1]
+
+
+class Curve:
+    """Projective points (X, Y, Z) over a field adaptor F with complete formulas."""
+
+    def __init__(self, F):
+        self.F = F
+        self.b = F.b
+
+    def neg(self, p):
+        return (p[0], -p[1], p[2])
+
+    def m(self, p):
+        return tuple(self.F.m(c) for c in p)
+
+    def add(self, p, q):
+        """Complete addition (RCB15 Alg. 7, a = 0).  p, q materialised."""
+        F = self.F
+        X1, Y1, Z1 = p
+        X2, Y2, Z2 = q
+        A = F.m(F.mul(X1, X2))
+        B = F.m(F.mul(Y1, Y2))
+        C = F.m(F.mul(Z1, Z2))
+        D = F.m(F.mul(X1, Y2) + F.mul(X2, Y1))
+        E = F.m(F.mul(Y1, Z2) + F.mul(Y2, Z1))
+        Fv = F.m(F.mul(X1, Z2) + F.mul(X2, Z1))
+        bC = F.m(F.mul_b3(C))
+        bF = F.m(F.mul_b3(Fv))
+        A3 = F.scale(A, 3)
+        X3 = F.mul(D, B - bC) - F.mul(E, bF)
+        Y3 = F.mul(B + bC, B - bC) + F.mul(A3, bF)
+        Z3 = F.mul(E, B + bC) + F.mul(A3, D)
+        return (F.m(X3), F.m(Y3), F.m(Z3))
+
+    def dbl(self, p):
+        """Complete doubling (RCB15 Alg. 9, a = 0)."""
+        F = self.F
+        X, Y, Z = p
+        YY = F.m(F.sqr(Y))
+        ZZ = F.m(F.sqr(Z))
+        XY = F.m(F.mul(X, Y))
+        YZ = F.m(F.mul(Y, Z))
+        bZZ = F.m(F.mul_b3(ZZ))
+        # X3 = 2 XY (YY - 3 bZZ) ; Y3 = (YY + bZZ)(YY - 3 bZZ) + 8 YY bZZ ; Z3 = 8 YY YZ
+        t = YY - F.scale(bZZ, 3)
+        X3 = F.mul(F.scale(XY, 2), t)
+        Y3 = F.mul(YY + bZZ, t) + F.mul(F.scale(YY, 4), F.scale(bZZ, 2))
+        Z3 = F.mul(F.scale(YY, 4), F.scale(YZ, 2))
+        return (F.m(X3), F.m(Y3), F.m(Z3))
+
+    def mul_fixed(self, p, k: int):
+        """[k]P for a public constant k (MSB-first double-and-add; complete formulas cover every case)."""
+        acc = p
+        for i in range(k.bit_length() - 2, -1, -1):
+            acc = self.dbl(acc)
+            if (k >> i) & 1:
+                acc = self.add(acc, p)
+        return acc
+
+    def mul_secret(self, p, bits):
+        """[sum bits_i 2^i]P for per-lane bit flags (LSB first): always double, always add, select."""
+        F = self.F
+        zero = (F.zero(), F.one(), F.zero())
+        acc = tuple(F.m(c) if not self._is_sym_zero(c) else c for c in zero)
+        acc = self._mat_point(zero)
+        for i in range(len(bits) - 1, -1, -1):
+            acc = self.dbl(acc)
+            t = self.add(acc, p)
+            acc = tuple(F.select(bits[i], tc, ac) for tc, ac in zip(t, acc))
+        return acc
+
+    def _is_sym_zero(self, c):
+        return False
+
+    def _mat_point(self, p):
+        """Materialise a point with possibly constant coordinates into slots (copy ops)."""
+        F, b = self.F, self.b
+        out = []
+        for c in p:
+            cs = []
+            for x in F.coeffs(c):
+                if isinstance(x, Lin) and x.is_zero():
+                    x = Lin.of(b.const_raw(0))
+                cs.append(Lin.of(b.mat(x)))
+            out.append(cs[0] if len(cs) == 1 else E2(cs[0], cs[1]))
+        return tuple(out)
+
+    def eq(self, p, q) -> Val:
+        """Projective equality (math.ts:915-927)."""
+        F, b = self.F, self.b
+        xe = F.is_zero(F.mul(p[0], q[2]) - F.mul(q[0], p[2]))
+        ye = F.is_zero(F.mul(p[1], q[2]) - F.mul(q[1], p[2]))
+        return b.flag_and(xe, ye)
+
+    def is_on_curve(self, p) -> Val:
+        """y^2 z - x^3 - b z^3 == 0  (index.ts:408-414 / 675-681)."""
+        F = self.F
+        X, Y, Z = p
+        XX = F.m(F.sqr(X))
+        YY = F.m(F.sqr(Y))
+        ZZ = F.m(F.sqr(Z))
+        return F.is_zero(F.mul(YY, Z) - F.mul(XX, X) - F.mul(F.mul_b(ZZ), Z))
+
+
+# ------------------------------------------------------------------------------------------ exponent chains
+def pow_fixed(mul, sqr, m, one, a, e: int, window: int = 4):
+    """a^e for a public exponent with a fixed window; `m` materialises, `one` is used only if e == 0."""
+    if e == 0:
+        return one
+    tab = [None, a]
+    for k in range(2, 1 << window):
+        tab.append(m(mul(tab[k - 1], a)))
+    digits = []
+    while e:
+        digits.append(e & ((1 << window) - 1))
+        e >>= window
+    digits.reverse()
+    acc = tab[digits[0]]
+    for d in digits[1:]:
+        for _ in range(window):
+            acc = m(sqr(acc))
+        if d:
+            acc = m(mul(acc, tab[d]))
+    return acc
+
+
+class Ingest:
+    """Builds the ingest programs on top of a Tower."""
+
+    def __init__(self, t: Tower):
+        self.t, self.b = t, t.b
+        self.F1, self.F2 = FpF(t), Fp2F(t)
+        self.G1, self.G2 = Curve(self.F1), Curve(self.F2)
+        # psi constants (math.ts:1390-1403 reduce to conj(x)*cx, conj(y)*cy)
+        from .tower import _fp2_pow, _fp2_mul
+        xi = (1, 1)
+        inv = lambda a: _fp2_pow(a, P * P - 2)
+        self.psi_cx = inv(_fp2_pow(xi, (P - 1) // 3))
+        self.psi_cy = inv(_fp2_pow(xi, (P - 1) // 2))
+        self.psi2_c1 = 0x1A0111EA397FE699EC02408663D4DE85AA0D857D89759AD4897D29650FB85F9B409427EB4F49FFFD8BFD00000000AAAC
+        self.cubic_root = 0x5F19672FDF76CE51BA69C6076A0F77EADDB3A93BE6F89688DE17D813620A00022E01FFFFFFFEFFFE
+
+    # ---- field helpers ---------------------------------------------------------------------------
+    def fp_sqrt_candidate(self, a: Lin) -> Lin:  # a^((p+1)/4)   math.ts:260-264
+        b = self.b
+        a = Lin.of(b.mat(a))
+        return pow_fixed(lambda x, y: x * y, lambda x: x * x, lambda q: Lin.of(b.mat(q)), self.t.fp_const(1), a, (P + 1) // 4)
+
+    def fp2_pow(self, a: E2, e: int) -> E2:
+        b = self.b
+        a = a.m(b)
+        return pow_fixed(lambda x, y: x * y, lambda x: x.sqr(), lambda q: q.m(b), self.F2.one(), a, e)
+
+    def fp2_eq(self, a: E2, c: E2) -> Val:
+        return self.F2.is_zero(a - c)
+
+    def flag_const(self, v: int) -> Lin:
+        return Lin.of(self.b.const_raw(v))
+
+    def status_chain(self, conds) -> Val:
+        """conds = [(flag, code), ...] in priority order (first true wins); else ST_OK."""
+        b = self.b
+        st = self.flag_const(ST_OK)
+        for flag, code in reversed(conds):
+            st = Lin.of(b.select(flag, self.flag_const(code), st))
+        return b.mat(st)
+
+    # ---- endomorphisms ---------------------------------------------------------------------------
+    def g2_psi(self, p):  # projective form of math.ts:1398-1403
+        X, Y, Z = p
+        return self.G2.m((self.t.mul_const2(X.conj(), self.psi_cx), self.t.mul_const2(Y.conj(), self.psi_cy), Z.conj()))
+
+    def g2_psi2(self, p):  # math.ts:1406-1408
+        X, Y, Z = p
+        return self.G2.m((X * self.t.fp_const(self.psi2_c1), -Y, Z))
+
+    def g1_is_torsion_free(self, p) -> Val:  # index.ts:444-448:  [x]([x]P) == -... : u2P = x^2 P == phi(P)
+        xP = self.G1.neg(self.G1.mul_fixed(p, X_PARAM))  # mulCurveX = -(|x| P)
+        u2P = self.G1.mul_fixed(self.G1.m(xP), X_PARAM)  # mulCurveMinusX
+        phi = self.G1.m((p[0] * self.t.fp_const(self.cubic_root), p[1], p[2]))
+        return self.G1.eq(u2P, phi)
+
+    def g2_is_torsion_free(self, p) -> Val:  # index.ts:688-690:  [-x]P == psi(P)
+        xP = self.G2.m(self.G2.neg(self.G2.mul_fixed(p, X_PARAM)))
+        return self.G2.eq(xP, self.g2_psi(p))
+
+    def g2_clear_cofactor(self, p):  # index.ts:659-672
+        G = self.G2
+        t1 = G.m(G.neg(G.mul_fixed(p, X_PARAM)))  # [-x]P
+        t2 = self.g2_psi(p)
+        t3 = self.g2_psi2(G.dbl(p))
+        t3 = G.add(t3, G.m(G.neg(t2)))
+        t2 = G.add(t1, t2)
+        t2 = G.m(G.neg(G.mul_fixed(t2, X_PARAM)))
+        t3 = G.add(t3, t2)
+        t3 = G.add(t3, G.m(G.neg(t1)))
+        return G.add(t3, G.m(G.neg(p)))
+
+    # ---- affine conversion ---------------------------------------------------------------------------
+    def g1_to_affine(self, p):
+        zi = self.t.fp_inv(p[2])
+        return Lin.of(self.b.mat(p[0] * zi)), Lin.of(self.b.mat(p[1] * zi))
+
+    def g2_to_affine(self, p):
+        zi = self.t.fp2_inv(p[2]).m(self.b)
+        return (p[0] * zi).m(self.b), (p[1] * zi).m(self.b)
+
+
+# ------------------------------------------------------------------------------------------ programs
+# Buffer conventions for the ingest programs (api.cu):
+#   g1_decompress : 0 = in  n x 48 B compressed      2 = out n x 96 B affine    5 = status n x int32
+#   g2_decompress : 0 = in  n x 96 B signature form  2 = out n x 192 B affine   5 = status n x int32
+BUF_IN, BUF_OUT, BUF_STATUS = 0, 2, 5
+
+# eighth roots of unity / etas used by the reference's Fp2 sqrt and SWU (math.ts:1415-1452)
+_RV1 = 0x6AF0E0437FF400B6831E36D6BD17FFE48395DABC2D3435E77F76E17009241C5EE67992F72EC05F4C81084FBEDE3CC09
+_EV = (
+    0x699BE3B8C6870965E5BF892AD5D2CC7B0E85A117402DFD83B7F4A947E02D978498255A2AAEC0AC627B5AFBDF1BF1C90,
+    0x8157CD83046453F5DD0972B6E3949E4288020B5B8A9CC99CA07E27089A2CE2436D965026ADAD3EF7BABA37F2183E9B5,
+    0xAB1C2FFDD6C253CA155231EB3E71BA044FD562F6F72BC5BAD5EC46A0B7A3B0247CF08CE6C6317F40EDBC653A72DEE17,
+    0xAA404866706722864480885D68AD0CCAC1967C7544B447873CC37E0181271E006DF72162A3D3E0287BF597FBF7F8FC1,
+)
+ROOTS_OF_UNITY_POS = [(1, 0), (_RV1, (-_RV1) % P), (0, 1), (_RV1, _RV1)]
+ETAS = [(_EV[0], _EV[1]), ((-_EV[1]) % P, _EV[0]), (_EV[2], _EV[3]), ((-_EV[3]) % P, _EV[2])]
+
+
+def _fp2_inv_const(a):
+    from .tower import _fp2_pow
+    return _fp2_pow(a, P * P - 2)
+
+
+def build_g1_decompress(warps=8) -> Builder:
+    """PointG1.fromHex for 48-byte compressed keys (index.ts:301-315, 325) incl. assertValidity."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    flag_inf = b.bit(BUF_IN, 0, 48, 382)
+    flag_sign = b.bit(BUF_IN, 0, 48, 381)
+    x = Lin.of(b.inp_bytes(BUF_IN, 0, 48, clear_top=3))
+    x2 = Lin.of(b.mat(x * x))
+    right = Lin.of(b.mat(x2 * x + t.fp_const(4)))  # y^2 = x^3 + b
+    cand = ig.fp_sqrt_candidate(right)
+    no_sqrt = b.flag_not(b.is_zero(cand * cand - right))
+    flip = b.flag_xor(b.gt_half(cand), flag_sign)  # (y*2)/P != aflag
+    y = Lin.of(b.select(flip, -cand, cand))
+    pt = (x, y, Lin.of(b.mat(t.fp_const(1))))
+    not_sub = b.flag_not(ig.g1_is_torsion_free(pt))
+    st = ig.status_chain([(flag_inf, ST_INFINITY), (no_sqrt, ST_BAD_ENCODING), (not_sub, ST_NOT_IN_SUBGROUP)])
+    b.out(x, BUF_OUT, 0)
+    b.out(y, BUF_OUT, 1)
+    b.out_word(st, BUF_STATUS)
+    return b
+
+
+def _fp2_sqrt_any(ig: Ingest, a: E2):
+    """Some square root of `a` (or garbage) and the flag `found`; candidates per math.ts:486-501."""
+    b, t = ig.b, ig.t
+    a = a.m(b)
+    c = ig.fp2_pow(a, (P * P + 8) // 16)
+    y = None
+    found = None
+    for root in ROOTS_OF_UNITY_POS:
+        yk = t.mul_const2(c, _fp2_inv_const(root)).m(b)
+        ok = ig.fp2_eq(yk.sqr(), a)
+        if y is None:
+            y, found = yk, ok
+        else:
+            y = ig.F2.select(ok, yk, y)
+            found = b.flag_or(ok, found)
+    return y, found
+
+
+def build_g2_decompress(warps=8) -> Builder:
+    """PointG2.fromSignature for 96-byte compressed signatures (index.ts:500-530) incl. assertValidity."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    flag_inf = b.bit(BUF_IN, 0, 48, 382)
+    aflag = b.bit(BUF_IN, 0, 48, 381)
+    x1 = Lin.of(b.inp_bytes(BUF_IN, 0, 48, clear_top=3))   # z1 mod 2^381  -> imaginary part
+    x0 = Lin.of(b.inp_bytes(BUF_IN, 48, 48))               # z2            -> real part
+    x = E2(x0, x1)
+    xx = x.sqr().m(b)
+    y2 = (xx * x + E2(t.fp_const(4), t.fp_const(4))).m(b)   # x^3 + 4(1+u)
+    y, found = _fp2_sqrt_any(ig, y2)
+    y = y.m(b)
+    y1_zero = b.is_zero(y.c1)
+    g1 = b.gt_half(y.c1)
+    g0 = b.gt_half(y.c0)
+    # isGreater = y1 > 0 && (y1*2)/P != aflag ; isZero = y1 == 0 && (y0*2)/P != aflag     (index.ts:522-526)
+    is_greater = b.flag_and(b.flag_not(y1_zero), b.flag_xor(g1, aflag))
+    is_zero = b.flag_and(y1_zero, b.flag_xor(g0, aflag))
+    flip = b.flag_or(is_greater, is_zero)
+    y = ig.F2.select(flip, -y, y)
+    pt = (x, y, E2(Lin.of(b.mat(t.fp_const(1))), Lin.of(b.mat(Lin.of(b.const_raw(0))))))
+    not_sub = b.flag_not(ig.g2_is_torsion_free(pt))
+    st = ig.status_chain([(flag_inf, ST_INFINITY), (b.flag_not(found), ST_NO_SQRT), (not_sub, ST_NOT_IN_SUBGROUP)])
+    b.out(x.c0, BUF_OUT, 0)
+    b.out(x.c1, BUF_OUT, 1)
+    b.out(y.c0, BUF_OUT, 2)
+    b.out(y.c1, BUF_OUT, 3)
+    b.out_word(st, BUF_STATUS)
+    return b
+
+
+PROGRAMS = {
+    "g1_decompress": build_g1_decompress,
+    "g2_decompress": build_g2_decompress,
+}
+
+
+# ------------------------------------------------------------------------------------------ hash to G2
+# 3-isogeny coefficients E' -> E (math.ts:1547-1610), leading coefficient first
+_ISO3 = {
+    "xnum": [
+        (0x171D6541FA38CCFAED6DEA691F5FB614CB14B4E7F4E810AA22D6108F142B85757098E38D0F671C7188E2AAAAAAAA5ED1, 0),
+        (0x11560BF17BAA99BC32126FCED787C88F984F87ADF7AE0C7F9A208C6B4F20A4181472AAA9CB8D555526A9FFFFFFFFC71E,
+         0x8AB05F8BDD54CDE190937E76BC3E447CC27C3D6FBD7063FCD104635A790520C0A395554E5C6AAAA9354FFFFFFFFE38D),
+        (0, 0x11560BF17BAA99BC32126FCED787C88F984F87ADF7AE0C7F9A208C6B4F20A4181472AAA9CB8D555526A9FFFFFFFFC71A),
+        (0x5C759507E8E333EBB5B7A9A47D7ED8532C52D39FD3A042A88B58423C50AE15D5C2638E343D9C71C6238AAAAAAAA97D6,
+         0x5C759507E8E333EBB5B7A9A47D7ED8532C52D39FD3A042A88B58423C50AE15D5C2638E343D9C71C6238AAAAAAAA97D6),
+    ],
+    "xden": [(0, 0), (1, 0), (12, P - 12), (0, P - 72)],
+    "ynum": [
+        (0x124C9AD43B6CF79BFBF7043DE3811AD0761B0F37A1E26286B0E977C69AA274524E79097A56DC4BD9E1B371C71C718B10, 0),
+        (0x11560BF17BAA99BC32126FCED787C88F984F87ADF7AE0C7F9A208C6B4F20A4181472AAA9CB8D555526A9FFFFFFFFC71C,
+         0x8AB05F8BDD54CDE190937E76BC3E447CC27C3D6FBD7063FCD104635A790520C0A395554E5C6AAAA9354FFFFFFFFE38F),
+        (0, 0x5C759507E8E333EBB5B7A9A47D7ED8532C52D39FD3A042A88B58423C50AE15D5C2638E343D9C71C6238AAAAAAAA97BE),
+        (0x1530477C7AB4113B59A4C18B076D11930F7DA5D4A07F649BF54439D87D27E500FC8C25EBF8C92F6812CFC71C71C6D706,
+         0x1530477C7AB4113B59A4C18B076D11930F7DA5D4A07F649BF54439D87D27E500FC8C25EBF8C92F6812CFC71C71C6D706),
+    ],
+    "yden": [(1, 0), (18, P - 18), (0, P - 216), (P - 432, P - 432)],
+}
+
+
+def _sgn0_fp2(ig: Ingest, x: E2) -> Val:  # math.ts:1179-1185
+    b = ig.b
+    x = x.m(b)
+    s0 = b.parity(x.c0)
+    z0 = b.is_zero(x.c0)
+    s1 = b.parity(x.c1)
+    return b.flag_or(s0, b.flag_and(z0, s1))
+
+
+def _swu_g2(ig: Ingest, tt: E2):
+    """map_to_curve_simple_swu_9mod16 (math.ts:1220-1267) returning the point of E' as (N : y*D : D)."""
+    b, t, F = ig.b, ig.t, ig.F2
+    A = (0, 240)
+    B = (1012, 1012)
+    Z = ((-2) % P, (-1) % P)
+    tt = tt.m(b)
+    t2 = tt.sqr().m(b)
+    z_t2 = t.mul_const2(t2, Z).m(b)
+    ztzt = (z_t2 + z_t2.sqr()).m(b)
+    den = (-t.mul_const2(ztzt, A)).m(b)
+    num = t.mul_const2(ztzt + E2(t.fp_const(1), Lin()), B).m(b)
+    den_zero = F.is_zero(den)
+    den = F.select(den_zero, t.e2_const(_fp2_mul_c(Z, A)).m(b) if False else _const_e2(ig, _fp2_mul_c(Z, A)), den)
+    d2 = den.sqr().m(b)
+    v = (d2 * den).m(b)
+    n2 = num.sqr().m(b)
+    u = (n2 * num + t.mul_const2((num * d2).m(b), A) + t.mul_const2(v, B)).m(b)
+    # sqrt_div_fp2(u, v)   (math.ts:1195-1214)
+    v2 = v.sqr().m(b)
+    v4 = v2.sqr().m(b)
+    v7 = ((v4 * v2).m(b) * v).m(b)
+    uv7 = (u * v7).m(b)
+    uv15 = (uv7 * (v7 * v).m(b)).m(b)
+    gamma = (ig.fp2_pow(uv15, (P * P - 9) // 16) * uv7).m(b)
+    y = gamma
+    success = None
+    for root in ROOTS_OF_UNITY_POS:
+        cand = t.mul_const2(gamma, root).m(b)
+        ok = F.is_zero((cand.sqr().m(b) * v).m(b) - u)
+        y = F.select(ok, cand, y)
+        success = ok if success is None else b.flag_or(ok, success)
+    # second candidate family (x1 = Z t^2 x0)
+    t3 = (t2 * tt).m(b)
+    sc_x1 = (gamma * t3).m(b)
+    zt2_3 = ((z_t2.sqr().m(b)) * z_t2).m(b)
+    u2 = (zt2_3 * u).m(b)
+    y2 = sc_x1
+    for eta in ETAS:
+        cand = t.mul_const2(sc_x1, eta).m(b)
+        ok = F.is_zero((cand.sqr().m(b) * v).m(b) - u2)
+        y2 = F.select(ok, cand, y2)
+    y = F.select(success, y, y2)
+    num = F.select(success, num, (num * z_t2).m(b))
+    flip = b.flag_xor(_sgn0_fp2(ig, tt), _sgn0_fp2(ig, y))
+    y = F.select(flip, -y, y)
+    return (num, (y * den).m(b), den)
+
+
+def _fp2_mul_c(a, c):
+    return ((a[0] * c[0] - a[1] * c[1]) % P, (a[0] * c[1] + a[1] * c[0]) % P)
+
+
+def _const_e2(ig: Ingest, pair) -> E2:
+    """Fp2 constant copied into slots (select needs slot operands of one kind)."""
+    b, t = ig.b, ig.t
+    return E2(Lin.of(b.mat(t.fp_const(pair[0]) if pair[0] % P else Lin.of(b.const_raw(0)))),
+              Lin.of(b.mat(t.fp_const(pair[1]) if pair[1] % P else Lin.of(b.const_raw(0)))))
+
+
+def _add_generic(ig: Ingest, p, q):
+    """add-1998-cmo-2 as coded in math.ts:1008-1024 (valid on the isogenous curve E' where a != 0; the
+    reference's special cases P == +-Q cannot be reached by two independent SWU outputs in practice)."""
+    b, F = ig.b, ig.F2
+    X1, Y1, Z1 = p
+    X2, Y2, Z2 = q
+    U1 = (Y2 * Z1).m(b)
+    U2 = (Y1 * Z2).m(b)
+    V1 = (X2 * Z1).m(b)
+    V2 = (X1 * Z2).m(b)
+    U = U1 - U2
+    V = V1 - V2
+    VV = V.sqr().m(b) if False else (V.m(b)).sqr().m(b)
+    Vm = V.m(b)
+    Um = U.m(b)
+    VVV = (VV * Vm).m(b)
+    V2VV = (V2 * VV).m(b)
+    W = (Z1 * Z2).m(b)
+    UU = Um.sqr().m(b)
+    Av = ((UU * W) - VVV - V2VV.scale(2)).m(b)
+    X3 = (Vm * Av).m(b)
+    Y3 = (Um * (V2VV - Av) - VVV * U2).m(b)
+    Z3 = (VVV * W).m(b)
+    return (X3, Y3, Z3)
+
+
+def _isogeny3_projective(ig: Ingest, p):
+    """isogenyMapG2 (math.ts:1315-1325) on a projective point of E', staying projective on E."""
+    b, t = ig.b, ig.t
+    X, Y, Z = p
+    X2 = X.sqr().m(b)
+    Z2 = Z.sqr().m(b)
+    X3 = (X2 * X).m(b)
+    Z3 = (Z2 * Z).m(b)
+    X2Z = (X2 * Z).m(b)
+    XZ2 = (X * Z2).m(b)
+    mono = [X3, X2Z, XZ2, Z3]
+
+    def poly(coeffs):
+        acc = None
+        for k, m_ in zip(coeffs, mono):
+            if k[0] % P == 0 and k[1] % P == 0:
+                continue
+            term = t.mul_const2(m_, k)
+            acc = term if acc is None else acc + term
+        return acc.m(b)
+
+    XN, XD, YN, YD = (poly(_ISO3[k]) for k in ("xnum", "xden", "ynum", "yden"))
+    YDZ = (YD * Z).m(b)
+    Xo = (XN * YDZ).m(b)
+    Yo = ((Y * YN).m(b) * XD).m(b)
+    Zo = (XD * YDZ).m(b)
+    return (Xo, Yo, Zo)
+
+
+def _hash_to_field_g2(ig: Ingest, buf: int):
+    """hash_to_field (index.ts:240-267) tail: four 64-byte big-endian chunks -> u0, u1 in Fp2."""
+    b, t = ig.b, ig.t
+    two256 = t.fp_const(1 << 256)
+    es = []
+    for j in range(4):
+        hi = Lin.of(b.inp_bytes(buf, 64 * j, 32))
+        lo = Lin.of(b.inp_bytes(buf, 64 * j + 32, 32))
+        es.append(Lin.of(b.mat(hi * two256 + lo)))
+    return E2(es[0], es[1]), E2(es[2], es[3])
+
+
+def _hash_to_g2_projective(ig: Ingest, buf: int):
+    """PointG2.hashToCurve (index.ts:481-490) from the 256 uniform bytes of expand_message_xmd."""
+    u0, u1 = _hash_to_field_g2(ig, buf)
+    p0 = _swu_g2(ig, u0)
+    p1 = _swu_g2(ig, u1)
+    s = _add_generic(ig, p0, p1)
+    e = _isogeny3_projective(ig, s)
+    return ig.g2_clear_cofactor(e)
+
+
+def build_hash_to_g2(warps=8) -> Builder:
+    """buffer 0: n x 256 B uniform bytes -> buffer 2: n x 192 B affine H(m) (x.c0, x.c1, y.c0, y.c1)."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    h = _hash_to_g2_projective(ig, BUF_IN)
+    x, y = ig.g2_to_affine(h)
+    b.out(x.c0, BUF_OUT, 0)
+    b.out(x.c1, BUF_OUT, 1)
+    b.out(y.c0, BUF_OUT, 2)
+    b.out(y.c1, BUF_OUT, 3)
+    return b
+
+
+PROGRAMS["hash_to_g2"] = build_hash_to_g2
