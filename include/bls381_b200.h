@@ -99,6 +99,29 @@ int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t
 int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
                         size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status);
 
+/* sign(message, privateKey) for byte messages                                   replaces index.ts:746-752
+ * (hashToCurve + constant-time scalar multiplication math.ts:1061-1078 + toSignature index.ts:586-598).
+ *   sks32: n x 32 B big-endian scalars already normalised to 0 < sk < r (normalizePrivKey index.ts:269-279 is
+ *   host-side argument checking); out_sig96: n x 96 B compressed signatures.                               */
+int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                      const uint8_t* dst, size_t dst_len, uint8_t* out_sig96);
+/* aggregatePublicKeys(Hex[]) / aggregateSignatures(Hex[])                       replaces index.ts:773-788
+ *   n compressed points in, one compressed point out; status[i] per input (any status other than OK / INFINITY
+ *   means the reference would have thrown while decoding that element).                                    */
+int bls381_aggregate_g1(const uint8_t* pks48, size_t n, uint8_t* out48, int32_t* status);
+int bls381_aggregate_g2(const uint8_t* sigs96, size_t n, uint8_t* out96, int32_t* status);
+/* PointG1#assertValidity / PointG2#assertValidity on affine points           replaces index.ts:383-388, 633-638
+ * (isOnCurve :408-414 / :675-681, isTorsionFree :444-448 / :688-690).  status: OK / NOT_ON_CURVE / NOT_IN_SUBGROUP */
+int bls381_g1_validate_batch(const uint8_t* g1_affine, size_t n, int32_t* status);
+int bls381_g2_validate_batch(const uint8_t* g2_affine, size_t n, int32_t* status);
+/* PointG2#multiply(scalar) (math.ts:1061-1078), used by sign(PointG2, key) index.ts:749-750.
+ *   scalars32: 0 < k <= r big-endian; out192 affine; flags[i] bit1 = result is the point at infinity          */
+int bls381_g2_scalar_mul_batch(const uint8_t* g2_affine, const uint8_t* scalars32, size_t n, uint8_t* out192,
+                               int32_t* flags);
+/* prod_i f_i in Fp12 (+ optional finalExponentiate): combines the per-GPU partial products of a sharded
+ * verifyBatch after the all-gather (index.ts:815-816).  in: n x 576 B, out: 576 B.                          */
+int bls381_fp12_product(const uint8_t* in_fp12, size_t n, int with_final_exp, uint8_t* out_fp12);
+
 /* Generic tower-VM launch (used by the tests and by the entry points above).
  *   program  : name of a loaded program ("pairing", "miller", "final_exp", ...)
  *   bufs     : up to 8 DEVICE buffers; strides[i] = bytes per item in buffer i                      */

@@ -37,6 +37,13 @@ def _load():
     lib.bls381_g1_decompress_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_g2_decompress_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_hash_to_g2_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_sign_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_aggregate_g1.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_aggregate_g2.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_fp12_product.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    lib.bls381_g1_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_g2_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_g2_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_verify_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     return lib
 
@@ -47,6 +54,8 @@ EXPORTS = [
     "bls381_miller_product", "bls381_miller_product_dev", "bls381_vm_run_dev", "bls381_vm_load",
     "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms",
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
+    "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
+    "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch",
 ]
 
 
@@ -115,6 +124,47 @@ class Engine:
         st = (ctypes.c_int32 * (n + 1))()
         self._check(self.lib.bls381_verify_batch(sig96, packed, off, pks48, n, dst, len(dst), ctypes.byref(v), st))
         return v.value, list(st)
+
+    def sign_batch(self, sks32: bytes, msgs, dst: bytes) -> bytes:
+        n = len(msgs)
+        assert len(sks32) == 32 * n
+        packed, off = self._pack(msgs)
+        out = ctypes.create_string_buffer(96 * n)
+        self._check(self.lib.bls381_sign_batch(sks32, packed, off, n, dst, len(dst), out))
+        return out.raw
+
+    def aggregate_g1(self, pks48: bytes, n: int):
+        out = ctypes.create_string_buffer(48)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_aggregate_g1(pks48, n, out, st))
+        return out.raw, list(st)
+
+    def aggregate_g2(self, sigs96: bytes, n: int):
+        out = ctypes.create_string_buffer(96)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_aggregate_g2(sigs96, n, out, st))
+        return out.raw, list(st)
+
+    def g1_validate_batch(self, g1: bytes, n: int):
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g1_validate_batch(g1, n, st))
+        return list(st)
+
+    def g2_validate_batch(self, g2: bytes, n: int):
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g2_validate_batch(g2, n, st))
+        return list(st)
+
+    def g2_scalar_mul_batch(self, g2: bytes, scalars32: bytes, n: int):
+        out = ctypes.create_string_buffer(192 * n)
+        fl = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g2_scalar_mul_batch(g2, scalars32, n, out, fl))
+        return out.raw, list(fl)
+
+    def fp12_product(self, f12: bytes, n: int, with_final_exp: bool = False) -> bytes:
+        out = ctypes.create_string_buffer(576)
+        self._check(self.lib.bls381_fp12_product(f12, n, int(with_final_exp), out))
+        return out.raw
 
     # ---- device-pointer entry points (ints = CUDA device addresses, e.g. torch tensor.data_ptr()) ----
     def pairing_batch_dev(self, d_g1: int, d_g2: int, n: int, with_final_exp: bool, d_out: int, stream: int = 0):

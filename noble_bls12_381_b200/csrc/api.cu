@@ -261,6 +261,50 @@ int hash_to_g2_dev(const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const
 const uint8_t kNegG1[96] = {  // -G1_BASE affine (x, p - y)
     0x17, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f, 0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58, 0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb, 0x11, 0x4d, 0x1d, 0x68, 0x55, 0xd5, 0x45, 0xa8, 0xaa, 0x7d, 0x76, 0xc8, 0xcf, 0x2e, 0x21, 0xf2, 0x67, 0x81, 0x6a, 0xef, 0x1d, 0xb5, 0x07, 0xc9, 0x66, 0x55, 0xb9, 0xd5, 0xca, 0xac, 0x42, 0x36, 0x4e, 0x6f, 0x38, 0xba, 0x0e, 0xcb, 0x75, 0x1b, 0xad, 0x54, 0xdc, 0xd6, 0xb9, 0x39, 0xc2, 0xca};
 
+// OR the compression flag bits (index.ts:26-28) into byte 0 of each compressed body
+__global__ void apply_flags_kernel(uint8_t* body, uint32_t stride, const int32_t* flags, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t f = flags[i];
+    uint8_t* p = body + i * stride;
+    if (f & 2) {  // point at infinity: 0xc0 00 .. 00
+        for (uint32_t k = 0; k < stride; ++k) p[k] = 0;
+        p[0] = 0xC0;
+    } else {
+        p[0] |= 0x80 | ((f & 1) << 5);
+    }
+}
+
+// sum of n affine points (+ status words: INFINITY = skip) -> compressed point at d_out (1 record)
+int aggregate_dev(bool g2, uint8_t* d_affine, int32_t* d_status, size_t n, uint8_t* d_out, cudaStream_t s) {
+    const uint32_t fe = g2 ? 96 : 48;       // bytes per coordinate
+    const uint32_t proj = 3 * fe;           // projective record
+    int rc;
+    size_t nb = (n + 31) / 32;
+    if ((rc = stage(2, nb * proj + proj)) || (rc = stage(3, ((nb + 31) / 32) * proj + proj)) || (rc = stage(5, 512))) return rc;
+    {
+        uint8_t* bufs[3] = {d_affine, reinterpret_cast<uint8_t*>(d_status), g.d_stage[2]};
+        uint32_t strides[3] = {2 * fe, 4, proj};
+        if ((rc = vm_run(g2 ? "g2_sum_affine" : "g1_sum_affine", bufs, strides, 3, n, s))) return rc;
+    }
+    uint8_t *cur = g.d_stage[2], *nxt = g.d_stage[3];
+    size_t count = nb;
+    while (count > 1) {
+        uint8_t* bufs[3] = {cur, nullptr, nxt};
+        uint32_t strides[3] = {proj, 0, proj};
+        if ((rc = vm_run(g2 ? "g2_sum_proj" : "g1_sum_proj", bufs, strides, 3, count, s))) return rc;
+        count = (count + 31) / 32;
+        std::swap(cur, nxt);
+    }
+    int32_t* d_flags = reinterpret_cast<int32_t*>(g.d_stage[5]);
+    uint8_t* bufs[6] = {cur, nullptr, d_out, nullptr, nullptr, reinterpret_cast<uint8_t*>(d_flags)};
+    uint32_t strides[6] = {proj, 0, fe, 0, 0, 4};
+    if ((rc = vm_run(g2 ? "g2_compress" : "g1_compress", bufs, strides, 6, 1, s))) return rc;
+    apply_flags_kernel<<<1, 32, 0, s>>>(d_out, fe, d_flags, 1);
+    CUDA_TRY(cudaGetLastError());
+    return BLS381_OK;
+}
+
 // ---- IMAD.WIDE issue-rate microbenchmark -------------------------------------------------------
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters) {
     uint64_t acc[4][6];
@@ -549,6 +593,139 @@ int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_
         else if (status[i] != BLS381_ST_OK) v = -1;
     }
     *verdict = v;
+    return BLS381_OK;
+}
+
+int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst,
+                      size_t dst_len, uint8_t* out_sig96) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!sks32 || !msg_off || !dst || !out_sig96) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    const size_t mbytes = msg_off[n];
+    if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(7, n * 32)) || (rc = stage(2, n * 96)) ||
+        (rc = stage(6, n * 4)) || (rc = stage(4, n * 256)) || (rc = stage(5, 512)))
+        return rc;
+    cudaStream_t s = g.stream;
+    std::vector<uint8_t> dp;
+    make_dst_prime(dst, dst_len, dp);
+    if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], sks32, n * 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[5], dp.data(), dp.size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(g.ev0, s));
+    xmd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, g.d_stage[5],
+                                                       (uint32_t)dp.size(), g.d_stage[4]);
+    CUDA_TRY(cudaGetLastError());
+    uint8_t* bufs[6] = {g.d_stage[4], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
+    uint32_t strides[6] = {256, 32, 96, 0, 0, 4};
+    if ((rc = vm_run("sign", bufs, strides, 6, n, s))) return rc;
+    apply_flags_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[2], 96, (const int32_t*)g.d_stage[6], n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(g.ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(out_sig96, g.d_stage[2], n * 96, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    return BLS381_OK;
+}
+
+static int aggregate_host(bool g2, const uint8_t* in, size_t n, uint8_t* out, int32_t* status) {
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in || !out || !status) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return fail(BLS381_EINVAL, "Expected non-empty array");
+    const uint32_t cb = g2 ? 96 : 48;
+    int rc;
+    if ((rc = stage(0, n * cb)) || (rc = stage(8, n * 2 * cb)) || (rc = stage(6, n * 4)) || (rc = stage(9, 256))) return rc;
+    cudaStream_t s = g.stream;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * cb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(g.ev0, s));
+    if ((rc = run3(g2 ? "g2_decompress" : "g1_decompress", g.d_stage[0], cb, g.d_stage[8], 2 * cb, (int32_t*)g.d_stage[6], n, s))) return rc;
+    if ((rc = aggregate_dev(g2, g.d_stage[8], (int32_t*)g.d_stage[6], n, g.d_stage[9], s))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[9], cb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    return BLS381_OK;
+}
+
+int bls381_aggregate_g1(const uint8_t* pks48, size_t n, uint8_t* out48, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return aggregate_host(false, pks48, n, out48, status);
+}
+
+int bls381_aggregate_g2(const uint8_t* sigs96, size_t n, uint8_t* out96, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return aggregate_host(true, sigs96, n, out96, status);
+}
+
+int bls381_fp12_product(const uint8_t* in_fp12, size_t n, int with_final_exp, uint8_t* out_fp12) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in_fp12 || !out_fp12) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return fail(BLS381_EINVAL, "empty batch");
+    int rc;
+    if ((rc = stage(2, n * 576 + 576)) || (rc = stage(3, ((n + 31) / 32) * 576 + 576)) || (rc = stage(8, 576))) return rc;
+    cudaStream_t s = g.stream;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[2], in_fp12, n * 576, cudaMemcpyHostToDevice, s));
+    uint8_t* res = nullptr;
+    if ((rc = product_tree(g.d_stage[2], n, g.d_stage[3], &res, s))) return rc;
+    if (with_final_exp) {
+        uint8_t* b2[4] = {nullptr, nullptr, g.d_stage[8], res};
+        uint32_t st2[4] = {0, 0, 576, 576};
+        if ((rc = vm_run("final_exp", b2, st2, 4, 1, s))) return rc;
+        res = g.d_stage[8];
+    }
+    CUDA_TRY(cudaMemcpyAsync(out_fp12, res, 576, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return BLS381_OK;
+}
+
+static int validate_host(bool g2, const uint8_t* in, size_t n, int32_t* status) {
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in || !status) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    const uint32_t ab = g2 ? 192 : 96;
+    int rc;
+    if ((rc = stage(0, n * ab)) || (rc = stage(6, n * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * ab, cudaMemcpyHostToDevice, g.stream));
+    if ((rc = run3(g2 ? "g2_validate" : "g1_validate", g.d_stage[0], ab, nullptr, 0, (int32_t*)g.d_stage[6], n, g.stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return BLS381_OK;
+}
+
+int bls381_g1_validate_batch(const uint8_t* g1_affine, size_t n, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return validate_host(false, g1_affine, n, status);
+}
+
+int bls381_g2_validate_batch(const uint8_t* g2_affine, size_t n, int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return validate_host(true, g2_affine, n, status);
+}
+
+int bls381_g2_scalar_mul_batch(const uint8_t* g2_affine, const uint8_t* scalars32, size_t n, uint8_t* out192, int32_t* flags) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!g2_affine || !scalars32 || !out192 || !flags) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    if ((rc = stage(0, n * 192)) || (rc = stage(7, n * 32)) || (rc = stage(2, n * 192)) || (rc = stage(6, n * 4))) return rc;
+    cudaStream_t s = g.stream;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], g2_affine, n * 192, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], scalars32, n * 32, cudaMemcpyHostToDevice, s));
+    uint8_t* bufs[6] = {g.d_stage[0], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
+    uint32_t strides[6] = {192, 32, 192, 0, 0, 4};
+    if ((rc = vm_run("g2_scalar_mul", bufs, strides, 6, n, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(flags, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return BLS381_OK;
 }
 

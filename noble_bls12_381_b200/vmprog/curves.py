@@ -170,20 +170,21 @@ class Curve:
                 acc = self.add(acc, p)
         return acc
 
-    def mul_secret(self, p, bits):
-        """[sum bits_i 2^i]P for per-lane bit flags (LSB first): always double, always add, select."""
-        F = self.F
-        zero = (F.zero(), F.one(), F.zero())
-        acc = tuple(F.m(c) if not self._is_sym_zero(c) else c for c in zero)
-        acc = self._mat_point(zero)
-        for i in range(len(bits) - 1, -1, -1):
+    def mul_secret(self, p, nbits: int, bit_fn):
+        """[k]P for a per-lane secret k: always double, always add, select on bit i (MSB first).  `bit_fn(i)`
+        creates the flag for bit i; it is fenced behind the previous iteration so that the 255 flags are
+        produced just in time instead of occupying slots from the start of the program."""
+        F, b = self.F, self.b
+        acc = self._mat_point((F.zero(), F.one(), F.zero()))
+        for i in range(nbits - 1, -1, -1):
             acc = self.dbl(acc)
+            fence = [c.t and list(c.t)[0].op for c in F.coeffs(acc[0]) if isinstance(c, Lin) and c.t]
+            b.set_after([op for op in fence if op is not None])
+            flag = bit_fn(i)
+            b.set_after([])
             t = self.add(acc, p)
-            acc = tuple(F.select(bits[i], tc, ac) for tc, ac in zip(t, acc))
+            acc = tuple(F.select(flag, tc, ac) for tc, ac in zip(t, acc))
         return acc
-
-    def _is_sym_zero(self, c):
-        return False
 
     def _mat_point(self, p):
         """Materialise a point with possibly constant coordinates into slots (copy ops)."""
@@ -607,3 +608,181 @@ def build_hash_to_g2(warps=8) -> Builder:
 
 
 PROGRAMS["hash_to_g2"] = build_hash_to_g2
+
+
+# ------------------------------------------------------------------------------------------ sign / aggregate
+BUF_AUX = 1  # second input buffer (scalars for `sign`, status words for the sums)
+
+
+def _g2_compress_out(ig: Ingest, p, buf_out=BUF_OUT, buf_flags=BUF_STATUS):
+    """toSignature (index.ts:586-598): x.c1 || x.c0 as 2 x 48 B plus a flag word (bit0 = sign flag aflag1,
+    bit1 = point at infinity); the host ORs the flags into the top bits of byte 0."""
+    b, t = ig.b, ig.t
+    is_inf = ig.F2.is_zero(p[2])
+    x, y = ig.g2_to_affine(p)
+    y1_zero = b.is_zero(y.c1)
+    aflag = b.select(y1_zero, Lin.of(b.gt_half(y.c0)), Lin.of(b.gt_half(y.c1)))
+    word = b.select(is_inf, Lin.of(b.const_raw(2)), Lin.of(aflag))
+    b.out(x.c1, buf_out, 0)
+    b.out(x.c0, buf_out, 1)
+    b.out_word(word, buf_flags)
+
+
+def _g1_compress_out(ig: Ingest, p, buf_out=BUF_OUT, buf_flags=BUF_STATUS):
+    """PointG1.toHex(true) (index.ts:359-371): x as 48 B plus flag word (bit0 = (y*2)/P, bit1 = infinity)."""
+    b = ig.b
+    is_inf = b.is_zero(p[2])
+    x, y = ig.g1_to_affine(p)
+    word = b.select(is_inf, Lin.of(b.const_raw(2)), Lin.of(b.gt_half(y)))
+    b.out(x, buf_out, 0)
+    b.out_word(word, buf_flags)
+
+
+def build_sign(warps=8) -> Builder:
+    """sign(message, privateKey) (index.ts:746-752): sk * H(m), compressed.
+    buffer 0: n x 256 B uniform bytes of expand_message_xmd; buffer 1: n x 32 B scalars (0 < sk < r, big-endian);
+    buffer 2: n x 96 B signature body; buffer 5: n x int32 flag words."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    h = _hash_to_g2_projective(ig, BUF_IN)
+    s = ig.G2.mul_secret(h, R_ORDER.bit_length(), lambda i: b.bit(BUF_AUX, 0, 32, i))
+    _g2_compress_out(ig, s)
+    return b
+
+
+def _lane_sum(ig: Ingest, G: Curve, p):
+    """Butterfly sum over the 32 lanes with complete additions (every lane ends with the total)."""
+    b, F = ig.b, G.F
+    for mask in (1, 2, 4, 8, 16):
+        other = []
+        for c in p:
+            cs = [Lin.of(b.xlane(b.mat(x), mask)) for x in F.coeffs(c)]
+            other.append(cs[0] if len(cs) == 1 else E2(cs[0], cs[1]))
+        p = G.add(p, tuple(other))
+    return p
+
+
+def _pad_identity(ig: Ingest, G: Curve, p, skip_flag=None):
+    """Padding lanes (and lanes flagged `skip_flag`) contribute the identity (0 : 1 : 0)."""
+    b, F = ig.b, G.F
+    one = b.const(1)
+    zero = b.const_raw(0)
+    ident_consts = [zero, one, zero]
+    out = []
+    for c, k in zip(p, ident_consts):
+        cs = F.coeffs(c)
+        sel = []
+        for j, x in enumerate(cs):
+            const = k if j == 0 else zero
+            v = b.mat(x if not (isinstance(x, Lin) and x.is_zero()) else Lin.of(zero))
+            if skip_flag is not None:
+                v = b.select(skip_flag, Lin.of(const), Lin.of(v))
+            sel.append(Lin.of(b.pad_select(v, const)))
+        out.append(sel[0] if len(sel) == 1 else E2(sel[0], sel[1]))
+    return tuple(out)
+
+
+def _build_sum(which: str, level: str, warps: int) -> Builder:
+    """Per-batch partial sums.  level 'affine': inputs are affine points (buffer 0) + status words (buffer 1, an
+    INFINITY status means 'skip'); level 'proj': inputs are projective partial sums (buffer 0).
+    Output (buffer 2, one record per 32-item batch): projective X, Y, Z."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    G = ig.G1 if which == "g1" else ig.G2
+    nf = 1 if which == "g1" else 2
+
+    def load(k):
+        if nf == 1:
+            return Lin.of(b.inp(BUF_IN, k))
+        return E2(Lin.of(b.inp(BUF_IN, 2 * k)), Lin.of(b.inp(BUF_IN, 2 * k + 1)))
+
+    if level == "affine":
+        one = Lin.of(b.mat(t.fp_const(1)))
+        z = one if nf == 1 else E2(one, Lin.of(b.mat(Lin.of(b.const_raw(0)))))
+        p = (load(0), load(1), z)
+        skip = b.bit(BUF_AUX, 0, 1, 0)  # status word INFINITY (1): point at infinity, contributes nothing
+        p = _pad_identity(ig, G, p, skip)
+    else:
+        p = _pad_identity(ig, G, (load(0), load(1), load(2)))
+    s = _lane_sum(ig, G, p)
+    k = 0
+    for c in s:
+        for x in G.F.coeffs(c):
+            b.out(x, BUF_OUT, k, per_batch=True)
+            k += 1
+    return b
+
+
+def _build_compress(which: str, warps: int) -> Builder:
+    """projective (buffer 0) -> compressed body (buffer 2) + flag word (buffer 5)."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    if which == "g1":
+        p = tuple(Lin.of(b.inp(BUF_IN, k)) for k in range(3))
+        _g1_compress_out(ig, p)
+    else:
+        p = tuple(E2(Lin.of(b.inp(BUF_IN, 2 * k)), Lin.of(b.inp(BUF_IN, 2 * k + 1))) for k in range(3))
+        _g2_compress_out(ig, p)
+    return b
+
+
+PROGRAMS.update({
+    "sign": build_sign,
+    "g1_sum_affine": lambda w: _build_sum("g1", "affine", w),
+    "g1_sum_proj": lambda w: _build_sum("g1", "proj", w),
+    "g2_sum_affine": lambda w: _build_sum("g2", "affine", w),
+    "g2_sum_proj": lambda w: _build_sum("g2", "proj", w),
+    "g1_compress": lambda w: _build_compress("g1", w),
+    "g2_compress": lambda w: _build_compress("g2", w),
+})
+
+
+# ------------------------------------------------------------------------------------------ validity / scalar mul
+def _build_validate(which: str, warps: int) -> Builder:
+    """assertValidity (index.ts:383-388 / 633-638) of affine points: buffer 0 affine in, buffer 5 status."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    one = Lin.of(b.mat(t.fp_const(1)))
+    if which == "g1":
+        p = (Lin.of(b.inp(BUF_IN, 0)), Lin.of(b.inp(BUF_IN, 1)), one)
+        G, tors = ig.G1, ig.g1_is_torsion_free
+    else:
+        z = E2(one, Lin.of(b.mat(Lin.of(b.const_raw(0)))))
+        p = (E2(Lin.of(b.inp(BUF_IN, 0)), Lin.of(b.inp(BUF_IN, 1))), E2(Lin.of(b.inp(BUF_IN, 2)), Lin.of(b.inp(BUF_IN, 3))), z)
+        G, tors = ig.G2, ig.g2_is_torsion_free
+    not_on = b.flag_not(G.is_on_curve(p))
+    not_sub = b.flag_not(tors(p))
+    st = ig.status_chain([(not_on, ST_NOT_ON_CURVE), (not_sub, ST_NOT_IN_SUBGROUP)])
+    b.out_word(st, BUF_STATUS)
+    return b
+
+
+def build_g2_scalar_mul(warps=4) -> Builder:
+    """ProjectivePoint#multiply(scalar) on G2 (math.ts:1061-1078): buffer 0 affine point, buffer 1 32-byte scalar
+    (0 < k <= r) -> buffer 2 affine result, buffer 5 flag word (bit1 = result is the point at infinity)."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    one = Lin.of(b.mat(t.fp_const(1)))
+    z = E2(one, Lin.of(b.mat(Lin.of(b.const_raw(0)))))
+    p = (E2(Lin.of(b.inp(BUF_IN, 0)), Lin.of(b.inp(BUF_IN, 1))), E2(Lin.of(b.inp(BUF_IN, 2)), Lin.of(b.inp(BUF_IN, 3))), z)
+    s = ig.G2.mul_secret(p, R_ORDER.bit_length(), lambda i: b.bit(BUF_AUX, 0, 32, i))
+    is_inf = ig.F2.is_zero(s[2])
+    x, y = ig.g2_to_affine(s)
+    b.out(x.c0, BUF_OUT, 0)
+    b.out(x.c1, BUF_OUT, 1)
+    b.out(y.c0, BUF_OUT, 2)
+    b.out(y.c1, BUF_OUT, 3)
+    b.out_word(b.select(is_inf, Lin.of(b.const_raw(2)), Lin.of(b.const_raw(0))), BUF_STATUS)
+    return b
+
+
+PROGRAMS.update({
+    "g1_validate": lambda w: _build_validate("g1", w),
+    "g2_validate": lambda w: _build_validate("g2", w),
+    "g2_scalar_mul": build_g2_scalar_mul,
+})
