@@ -99,6 +99,12 @@ int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t
 int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
                         size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status);
 
+/* One shard of verifyBatch for multi-GPU runs: the un-exponentiated product of the shard's Miller
+ * loops e(pk_i, H(m_i)), times e(-G1, sig) when sig96_or_null != NULL (rank 0).  Partials of all ranks are
+ * all-gathered and combined with bls381_fp12_product(..., with_final_exp = 1).  status: n (+1 with a signature). */
+int bls381_verify_batch_partial(const uint8_t* sig96_or_null, const uint8_t* msgs, const uint64_t* msg_off,
+                                const uint8_t* pks48, size_t n, const uint8_t* dst, size_t dst_len,
+                                uint8_t* out_fp12, int32_t* status);
 /* sign(message, privateKey) for byte messages                                   replaces index.ts:746-752
  * (hashToCurve + constant-time scalar multiplication math.ts:1061-1078 + toSignature index.ts:586-598).
  *   sks32: n x 32 B big-endian scalars already normalised to 0 < sk < r (normalizePrivKey index.ts:269-279 is

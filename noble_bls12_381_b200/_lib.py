@@ -44,6 +44,7 @@ def _load():
     lib.bls381_g1_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_g2_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_g2_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_verify_batch_partial.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_verify_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     return lib
 
@@ -55,7 +56,7 @@ EXPORTS = [
     "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms",
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
     "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
-    "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch",
+    "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_verify_batch_partial",
 ]
 
 
@@ -124,6 +125,16 @@ class Engine:
         st = (ctypes.c_int32 * (n + 1))()
         self._check(self.lib.bls381_verify_batch(sig96, packed, off, pks48, n, dst, len(dst), ctypes.byref(v), st))
         return v.value, list(st)
+
+    def verify_batch_partial(self, sig96, msgs, pks48: bytes, dst: bytes):
+        """-> (576-byte un-exponentiated product of this shard, status list)"""
+        n = len(msgs)
+        packed, off = self._pack(msgs)
+        np_ = n + (1 if sig96 is not None else 0)
+        out = ctypes.create_string_buffer(576)
+        st = (ctypes.c_int32 * max(np_, 1))()
+        self._check(self.lib.bls381_verify_batch_partial(sig96, packed, off, pks48, n, dst, len(dst), out, st))
+        return out.raw, list(st)[:np_]
 
     def sign_batch(self, sks32: bytes, msgs, dst: bytes) -> bytes:
         n = len(msgs)

@@ -544,44 +544,61 @@ int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t
     return BLS381_OK;
 }
 
+// Shared body of verifyBatch: product of the Miller loops e(pk_i, H(m_i)) of n items [times e(-G1, sig) when
+// sig96 != NULL], optionally followed by the final exponentiation.  Result: 576 bytes at `out` (host).
+static int verify_partial(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
+                          size_t n, const uint8_t* dst, size_t dst_len, int with_final_exp, uint8_t* out, int32_t* status) {
+    int rc;
+    const size_t mbytes = n ? msg_off[n] : 0;
+    const size_t np = n + (sig96 ? 1 : 0);
+    if (np == 0) return fail(BLS381_EINVAL, "empty batch");
+    // staging: 0 msgs, 1 offsets, 7 pks(48) + sig(96), 8 result + g1 pairs, 9 g2 pairs, 6 status (n+1)
+    if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(7, n * 48 + 96)) ||
+        (rc = stage(8, (n + 1) * 96 + 576)) || (rc = stage(9, (n + 1) * 192)) || (rc = stage(6, (n + 1) * 4)))
+        return rc;
+    cudaStream_t s = g.stream;
+    uint8_t* d_g1 = g.d_stage[8] + 576;  // first 576 B: result
+    uint8_t* d_g2 = g.d_stage[9];
+    int32_t* d_st = (int32_t*)g.d_stage[6];
+    if (n) {
+        if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], pks48, n * 48, cudaMemcpyHostToDevice, s));
+    }
+    if (sig96) CUDA_TRY(cudaMemcpyAsync(g.d_stage[7] + n * 48, sig96, 96, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(g.ev0, s));
+    if (n) {
+        // publicKeys.map(normP1)  (index.ts:801)
+        if ((rc = run3("g1_decompress", g.d_stage[7], 48, d_g1, 96, d_st, n, s))) return rc;
+        // messages.map(normP2Hash)  (index.ts:800)
+        if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, d_g2, s))) return rc;
+    }
+    if (sig96) {
+        // normP2(signature)  (index.ts:799) and the pairing(G1.negate(), sig) term (index.ts:814)
+        if ((rc = run3("g2_decompress", g.d_stage[7] + n * 48, 96, d_g2 + n * 192, 192, d_st + n, 1, s))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_g1 + n * 96, kNegG1, 96, cudaMemcpyHostToDevice, s));
+    }
+    // product of the Miller loops (+ one final exponentiation)  (index.ts:812-816)
+    if ((rc = miller_product_dev(d_g1, d_g2, np, with_final_exp, g.d_stage[8], s))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[8], 576, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, d_st, np * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
+    return BLS381_OK;
+}
+
 int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
                         size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
     if (!sig96 || !msg_off || !pks48 || !dst || !verdict || !status) return fail(BLS381_EINVAL, "null argument");
     if (n == 0) return fail(BLS381_EINVAL, "Expected non-empty messages array");
-    int rc;
-    const size_t mbytes = msg_off[n];
-    // staging: 0 msgs, 1 offsets, 7 pks(48) + sig(96), 8 g1 pairs (n+1) x 96, 9 g2 pairs (n+1) x 192, 6 status (n+1)
-    if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(7, n * 48 + 96)) ||
-        (rc = stage(8, (n + 1) * 96 + 576)) || (rc = stage(9, (n + 1) * 192)) || (rc = stage(6, (n + 1) * 4)))
-        return rc;
-    cudaStream_t s = g.stream;
-    if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], pks48, n * 48, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(g.d_stage[7] + n * 48, sig96, 96, cudaMemcpyHostToDevice, s));
-    uint8_t* d_g1 = g.d_stage[8] + 576;  // first 576 B: result
-    uint8_t* d_g2 = g.d_stage[9];
-    int32_t* d_st = (int32_t*)g.d_stage[6];
-    CUDA_TRY(cudaEventRecord(g.ev0, s));
-    // publicKeys.map(normP1)  (index.ts:801)
-    if ((rc = run3("g1_decompress", g.d_stage[7], 48, d_g1, 96, d_st, n, s))) return rc;
-    // normP2(signature)  (index.ts:799)
-    if ((rc = run3("g2_decompress", g.d_stage[7] + n * 48, 96, d_g2 + n * 192, 192, d_st + n, 1, s))) return rc;
-    // messages.map(normP2Hash)  (index.ts:800)
-    if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, d_g2, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_g1 + n * 96, kNegG1, 96, cudaMemcpyHostToDevice, s));
-    // product of the n + 1 Miller loops and one final exponentiation (index.ts:812-816)
-    if ((rc = miller_product_dev(d_g1, d_g2, n + 1, 1, g.d_stage[8], s))) return rc;
-    CUDA_TRY(cudaEventRecord(g.ev1, s));
     uint8_t res[576];
-    CUDA_TRY(cudaMemcpyAsync(res, g.d_stage[8], 576, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(status, d_st, (n + 1) * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
-    g.last_ms = ms;
+    int rc = verify_partial(sig96, msgs, msg_off, pks48, n, dst, dst_len, 1, res, status);
+    if (rc) return rc;
     bool one = res[47] == 1;
     for (int i = 0; i < 576 && one; ++i)
         if (i != 47 && res[i] != 0) one = false;
@@ -594,6 +611,15 @@ int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_
     }
     *verdict = v;
     return BLS381_OK;
+}
+
+int bls381_verify_batch_partial(const uint8_t* sig96_or_null, const uint8_t* msgs, const uint64_t* msg_off,
+                                const uint8_t* pks48, size_t n, const uint8_t* dst, size_t dst_len, uint8_t* out_fp12,
+                                int32_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!dst || !out_fp12 || !status || (n && (!msg_off || !pks48))) return fail(BLS381_EINVAL, "null argument");
+    return verify_partial(sig96_or_null, msgs, msg_off, pks48, n, dst, dst_len, 0, out_fp12, status);
 }
 
 int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst,

@@ -122,3 +122,28 @@ def test_verify_batch_truth_table(eng, O):
     assert O.verify_batch(agg, msgs[:6], pks[:6]) is False
     assert O.verify_batch(O.aggregate_signatures(sigs[:6]), msgs[:6], pks[:6]) is True
     assert eng.verify_batch(O.aggregate_signatures(sigs[:6]), msgs[:6], b"".join(pks[:6]), dst)[0] == 1
+
+
+def test_sharded_partials_equal_fused_verify_batch(eng, O):
+    """Config-5 building blocks on one GPU: shard partials + fp12_product == fused verifyBatch, for 1/2/4/8 shards."""
+    from noble_bls12_381_b200 import dist as bdist
+    n = 24
+    msgs, sigs, pks = _signed_batch(O, n)
+    agg = O.aggregate_signatures(sigs)
+    dst = O.DEFAULT_DST
+    be = bdist.EngineBackend(eng)
+    ref = None
+    for world in (1, 2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = bdist.shard_range(n, r, world)
+            p, st = be.partial(agg if r == 0 else None, msgs[lo:hi], b"".join(pks[lo:hi]), dst) if (hi > lo or r == 0) else (bdist.FP12_ONE, [])
+            assert all(s == 0 for s in st)
+            parts.append(p)
+        res = be.combine(parts, True)
+        assert res == bdist.FP12_ONE
+        raw = be.combine(parts, False)
+        ref = ref or raw
+        assert raw == ref  # identical un-exponentiated product regardless of the shard count
+    v, _ = bdist.verify_batch_sharded(be, agg, msgs, pks, dst)
+    assert v == 1
