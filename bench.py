@@ -53,32 +53,27 @@ def _clocks_summary(samples):
             "reasons": sorted(reasons), "samples": len(samples)}
 
 
-def _oracle_worker(args):
-    """CPU baseline worker: the oracle's pairing (line precompute + Miller + final exp) on `count` items."""
-    start, count = args
-    from oracle import noble_oracle as O
-    p = O.pt_multiply_unsafe(O.G1, O.G1_BASE, start + 1)
-    q = O.pt_multiply_unsafe(O.G2, O.G2_BASE, start + 1)
-    t = time.perf_counter()
-    for _ in range(count):
-        pa, qa = O.pt_to_affine(O.G1, p), O.pt_to_affine(O.G2, q)
-        O.fp12_final_exponentiate(O.miller_loop(O.calc_pairing_precomputes(*qa), pa))
-        p = O.pt_add(O.G1, p, O.G1_BASE)
-        q = O.pt_add(O.G2, q, O.G2_BASE)
-    return count, time.perf_counter() - t
-
-
-def cpu_baseline(per_core: int):
-    """Oracle (Python port of the reference algorithm) on all host cores; returns (pairings/s, cores, n)."""
-    import multiprocessing as mp
+def cpu_baseline(total: int):
+    """The reference's algorithm on all host cores: the plain-C port of math.ts/index.ts (oracle/c, 64-bit limbs,
+    the reference's own Karatsuba tower formulas; pinned to the reference's golden vectors), one thread per core,
+    on `total` pairings of the bench workload.  Returns (pairings/s, cores, n)."""
+    from noble_bls12_381_b200 import synth
+    from oracle import c_oracle
     cores = os.cpu_count() or 1
-    cores = min(cores, 64)
-    t = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_oracle_worker, [(1000 * i, per_core) for i in range(cores)])
-    wall = time.perf_counter() - t
-    n = sum(r[0] for r in res)
-    return n / wall, cores, n
+    g1, g2 = synth.multiples_wire(total)
+    w = min(total, cores * 32)
+    c_oracle.pairing_batch(g1[: 96 * w], g2[: 192 * w], w, True, cores)  # warm-up: tables + CPU clocks
+    wall = None
+    for _ in range(2):  # best of two passes (the first seconds after an idle period run at a reduced CPU clock)
+        t = time.perf_counter()
+        out = c_oracle.pairing_batch(g1, g2, total, True, cores)
+        dt = time.perf_counter() - t
+        wall = dt if wall is None else min(wall, dt)
+    gold_path = os.path.join(ROOT, "tests", "golden", "pairing_kilic_1000.bin")
+    if os.path.exists(gold_path):
+        k = min(total, 1000)
+        assert out[: 576 * k] == open(gold_path, "rb").read()[: 576 * k], "CPU baseline output differs from the reference fixtures"
+    return total / wall, cores, total
 
 
 def run_reference(args):
@@ -86,13 +81,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_core = 6
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 160, 1024)
     for _ in range(args.warmup and 1):
-        cpu_baseline(1)
+        cpu_baseline(cores)
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, cores, n = cpu_baseline(per_core)
+        v, cores, n = cpu_baseline(per_step)
         vals.append(v)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = sum(vals) / len(vals)
@@ -103,7 +99,7 @@ def run_reference(args):
         "config": {"workload": "config 2: independent pairings e(i*G1, i*G2), Miller loop + final exponentiation",
                    "items_per_step": n},
         "cpu_baseline": {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_core} pairings per core per step, Python-int restatement of math.ts/index.ts (node/tsc absent on this image)"},
+                         "sample": f"{n} pairings per step ({n // cores} per core), plain-C port of math.ts/index.ts with the reference's own tower formulas, one thread per core (node/tsc absent on this image; index.ts:719 implies ~43 pairings/s/core for the TypeScript original)"},
         "e2e": {"value": v, "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -179,11 +175,14 @@ def verify_section(eng, n, rank, world, dist, torch):
     # negative control: one flipped message byte must give false
     bad = list(msgs)
     bad[n // 2] = bytes([bad[n // 2][0] ^ 1]) + bad[n // 2][1:]
-    neg_partial, _ = be.partial(agg if rank == 0 else None, bad[: min(n, 2048)], b"".join(pks[: min(n, 2048)]), dst)
+    k = min(n, 1024)
+    pos_partial, _ = be.partial(None, msgs[:k], b"".join(pks[:k]), dst)
+    bad2 = list(msgs[:k]); bad2[k // 2] = bad[n // 2]
+    neg_partial, _ = be.partial(None, bad2, b"".join(pks[:k]), dst)
     return {
         "metric": "verifyBatch sigs/sec (end to end, host buffers, sharded by index, one all-gather of W x 576 B)",
         "value": world * n / dt, "unit": "sigs/s", "sigs_per_gpu": n, "n_gpus": world, "ms": dt * 1e3,
-        "verdict_true": bool(ok), "negative_control_differs": neg_partial != b"",
+        "verdict_true": bool(ok), "negative_control_differs": neg_partial != pos_partial,
         "sign": {"value": n / sign_s, "unit": "sigs/s per GPU (host buffers)", "kernel_ms": sign_kernel_ms,
                  "note": "hash-to-curve + constant-time G2 scalar multiplication + compression on device"},
         "aggregate_signatures": {"value": n / agg_s, "unit": "sigs/s per GPU (decompress + validate + tree sum)"},
@@ -328,9 +327,9 @@ def main():
         if vb is not None:
             line["verify_batch"] = vb
         if not args.no_cpu_baseline:
-            v, cores, cnt = cpu_baseline(4)
+            v, cores, cnt = cpu_baseline(max((os.cpu_count() or 1) * 160, 1024))
             line["cpu_baseline"] = {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cnt} pairings (4 per core), Python-int restatement of math.ts/index.ts; reference comment index.ts:719 implies ~43/s/core on V8"}
+                                    "sample": f"{cnt} pairings of the same workload ({cnt // cores} per core), plain-C port of math.ts/index.ts (oracle/c, reference's Karatsuba tower formulas), one thread per core, outputs checked against the reference fixtures; the TypeScript original is ~43 pairings/s/core by its own comment (index.ts:719)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
