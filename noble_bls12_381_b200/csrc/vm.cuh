@@ -22,6 +22,7 @@
 #pragma once
 #include <cstdint>
 #include "fp_core.cuh"
+#include "fp_inv.cuh"
 
 namespace vm {
 
@@ -38,6 +39,7 @@ static constexpr int kConstSlots = 64;
 //                  [29] pad_const (padding lanes yield constant aux[31:24])  [27] dst_word (int32 store)
 //                  [30] post_iszero  [31] post_gt_half  (turn the canonical result into a 0/1 flag)
 // opcode OP_SEL  : dst = flag ? A : B  (word 2 = flag operand, word 3 = A operand, word 4 = B operand)
+// opcode OP_INV  : dst = (operand in word 2)^-1 mod p, Montgomery form (binary GCD, fp_inv.cuh; 0 -> 0)
 // opcode OP_BIT  : dst = bit `word 3` (0 = least significant) of the big-endian field of `word 4` bytes at
 //                  the GLOBAL operand in word 2
 // word 1 (aux)   : [7:0] dst buffer id  [15:8] dst field   [23:16] lane xor mask (for XLANE terms)
@@ -53,7 +55,7 @@ static constexpr int kConstSlots = 64;
 //                       bits to clear (compression flags), cB = 0: 48-byte field, 1: 32-byte field)
 //                  bit2 XLANE  (read the slot column of lane ^ mask)
 //                  bit3 SIMPLE (operand is exactly one shared-memory slot, coefficient +1: fast path)
-enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3 };
+enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3, OP_INV = 4 };
 enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8 };
 static constexpr uint32_t H_BAR = 1u << 25;
 static constexpr uint32_t H_DSTG = 1u << 26;
@@ -252,6 +254,10 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
         for (int k = 0; k < 12; ++k) any |= f[k];
 #pragma unroll
         for (int k = 0; k < 12; ++k) r[k] = any ? r[k] : b2[k];
+    } else if (op == OP_INV) {
+        uint32_t xin[12];
+        load_operand(xin, c, W(2), xmask);
+        fpc::fp_inv_mont(r, xin);
     } else if (op == OP_BIT) {
         const uint32_t w2 = W(2), bit = W(3), nbytes = W(4);
         const Buffer& bf = c.buf[w2 & 0xFF];

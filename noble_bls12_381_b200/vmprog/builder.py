@@ -27,7 +27,7 @@ R_MOD_P = R % P
 R2_MOD_P = R * R % P
 P_OVER_R = P / R  # ~0.1016
 
-OP_NOP, OP_MAC, OP_SEL, OP_BIT = 0, 1, 2, 3
+OP_NOP, OP_MAC, OP_SEL, OP_BIT, OP_INV = 0, 1, 2, 3, 4
 F_CONST, F_GLOBAL, F_XLANE, F_SIMPLE = 1, 2, 4, 8
 H_BAR, H_DSTG, H_DSTWORD, H_DSTBATCH, H_PADCONST, H_POST_ISZERO, H_POST_GTHALF = 1 << 25, 1 << 26, 1 << 27, 1 << 28, 1 << 29, 1 << 30, 1 << 31
 REC_WORDS = 32
@@ -188,6 +188,8 @@ class Op:
     def cost(self):
         """Estimated duration in units of one 12x12 product (calibrated on the ncu instruction counts: a
         product ~300 issued instructions, per-op reduction/correction/decode overhead ~500)."""
+        if self.kind == "inv":
+            return 235.0  # 25 outer iterations of the binary GCD, ~55 k instructions
         if self.kind != "mac":
             return 0.5
         t = len(self.terms)
@@ -329,6 +331,14 @@ class Builder:
         op = self._new_op([], [], ncorr)
         op.kind = "sel"
         op.sel = [of, oa, ob]
+        return op.out
+
+    def inv(self, e) -> Val:
+        """1/e mod p in ONE micro-op (binary GCD in registers, csrc/fp_inv.cuh); inv(0) = 0."""
+        v = self.mat(e)
+        op = self._new_op([], [], 0)
+        op.kind = "inv"
+        op.sel = [self._operand(Lin.of(v))]
         return op.out
 
     def bit(self, buf: int, byte_off: int, nbytes: int, bitindex: int) -> Val:
@@ -519,6 +529,9 @@ class Builder:
                 if op.kind == "sel":
                     f, a_, b_ = (ev_operand(o, lane, op.xmask) for o in op.sel)
                     r = a_ if f else b_
+                elif op.kind == "inv":
+                    x_ = ev_operand(op.sel[0], lane, op.xmask) % P  # Montgomery form a*R
+                    r = pow(x_ * rinv % P, -1, P) * R % P if x_ else 0
                 elif op.kind == "bit":
                     buf, off16, nbytes, bitindex = op.bit
                     r = (inputs[(buf, off16)][lane] >> bitindex) & 1
@@ -781,7 +794,7 @@ class Builder:
                 op = self.ops[i]
                 words = [0] * REC_WORDS
                 dst = 0 if op.dst_global is not None else self.slot_of[op.out.id]
-                opcode = {"mac": OP_MAC, "sel": OP_SEL, "bit": OP_BIT}[op.kind]
+                opcode = {"mac": OP_MAC, "sel": OP_SEL, "bit": OP_BIT, "inv": OP_INV}[op.kind]
                 hdr = opcode | (dst << 8) | (len(op.terms) << 16) | (len(op.epi) << 20) | (op.ncorr << 22)
                 if op.post == "iszero":
                     hdr |= H_POST_ISZERO
@@ -808,6 +821,8 @@ class Builder:
                     words[26 + 2 * e] = self._enc_operand(z)
                 if op.kind == "sel":
                     words[2], words[3], words[4] = (self._enc_operand(o) for o in op.sel)
+                elif op.kind == "inv":
+                    words[2] = self._enc_operand(op.sel[0])
                 elif op.kind == "bit":
                     buf, off16, nbytes, bitindex = op.bit
                     words[2], words[3], words[4] = buf | (off16 << 8), bitindex, nbytes

@@ -251,27 +251,9 @@ class Tower:
 
     # ---- inversion -------------------------------------------------------------------------------
     def fp_inv(self, a: Lin) -> Lin:
-        """a^(p-2) by a fixed 4-bit-window chain (any algorithm yields the same canonical residue as
-        the reference's extended Euclid, math.ts:134-156)."""
-        b = self.b
-        a = Lin.of(b.mat(a))
-        # table a^1..a^15
-        tab = [None, a]
-        for k in range(2, 16):
-            tab.append(Lin.of(b.mat(tab[k - 1] * a)))
-        e = P - 2
-        nibbles = []
-        while e:
-            nibbles.append(e & 15)
-            e >>= 4
-        nibbles.reverse()
-        acc = tab[nibbles[0]]
-        for nb in nibbles[1:]:
-            for _ in range(4):
-                acc = Lin.of(b.mat(acc * acc))
-            if nb:
-                acc = Lin.of(b.mat(acc * tab[nb]))
-        return acc
+        """1/a in one micro-op (fixed-iteration binary GCD, csrc/fp_inv.cuh).  Any algorithm yields the same
+        canonical residue as the reference's extended Euclid (math.ts:134-156)."""
+        return Lin.of(self.b.inv(a))
 
     def fp2_inv(self, a: E2) -> E2:  # math.ts:522-526
         b = self.b

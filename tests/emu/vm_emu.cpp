@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "../../noble_bls12_381_b200/csrc/vm.cuh"
+#include "../../noble_bls12_381_b200/csrc/fp_inv.cuh"
 
 extern "C" {
 
@@ -21,6 +22,9 @@ void emu_mac_redc(int n, const uint32_t* a, const uint32_t* b, int rounds, uint3
     fpc::acc_redc(A, r);
     fpc::correct(r, rounds);
 }
+
+// n Montgomery-form inversions (fp_inv.cuh)
+void emu_fp_inv(int n, const uint32_t* x, uint32_t* r) { for (int i = 0; i < n; ++i) fpc::fp_inv_mont(r + 12 * i, x + 12 * i); }
 
 void emu_add_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::add_mod(r, a, b); }
 void emu_sub_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::sub_mod(r, a, b); }
