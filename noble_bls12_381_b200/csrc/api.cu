@@ -42,6 +42,7 @@ struct State {
     std::atomic<uint64_t> launches{0};
     std::string program_dir;
     int force_ctas = 0;  // tuning override (env BLS381_B200_CTAS)
+    int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
 };
 
 State g;
@@ -71,7 +72,7 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6];
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
-    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
@@ -150,6 +151,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     L.nslots = p->nslots;
     L.nfar = std::max<uint32_t>(p->nfar, 1);
     L.n_items = (uint32_t)n;
+    L.pad = (uint32_t)g.sleep_ns;
     L.far = g.d_far;
     for (int i = 0; i < nbuf; ++i) {
         L.buf[i].base = bufs[i];
@@ -161,6 +163,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     if (p->warps == 4) return launch_w<4, 4>(L, grid, smem, s);
     if (p->warps == 6) return launch_w<6, 2>(L, grid, smem, s);
     if (p->warps == 8) return launch_w<8, 2>(L, grid, smem, s);
+    if (p->warps == 10) return launch_w<10, 2>(L, grid, smem, s);
     return fail(BLS381_EPROGRAM, "unsupported warp count");
 }
 
@@ -357,6 +360,7 @@ int bls381_init(int device, const char* program_dir) {
         }
     }
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
+    if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g.ev0));
     CUDA_TRY(cudaEventCreate(&g.ev1));

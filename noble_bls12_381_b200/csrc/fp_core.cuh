@@ -43,8 +43,9 @@ FPC_DEV void zero12(uint32_t* r) {
     for (int i = 0; i < 12; ++i) r[i] = 0;
 }
 
-// bring a value < 2^rounds * p (rounds <= 3) into [0, p)
+// bring a value < min(2^rounds * p, 2^384) (rounds <= 4) into [0, p)
 FPC_DEV void correct(uint32_t* r, int rounds) {
+    if (rounds >= 4) csub_8p(r);
     if (rounds >= 3) csub_4p(r);
     if (rounds >= 2) csub_2p(r);
     if (rounds >= 1) csub_1p(r);

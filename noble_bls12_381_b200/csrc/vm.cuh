@@ -43,7 +43,8 @@ static constexpr int kConstSlots = 64;
 // opcode OP_BIT  : dst = bit `word 3` (0 = least significant) of the big-endian field of `word 4` bytes at
 //                  the GLOBAL operand in word 2
 // word 1 (aux)   : [7:0] dst buffer id  [15:8] dst field   [23:16] lane xor mask (for XLANE terms)
-//                  [31:24] constant index for pad_const
+//                  [31:24] constant index for pad_const; otherwise post-scale factor k (0/1 = none): the reduced
+//                  sum of products is multiplied by k in {2,3,4} before the epilogue operands are added
 // words 2..25    : T terms, 2 words each:
 //     word A: [7:0] xA  [15:8] xB  [19:16] cA (signed 4-bit)  [23:20] cB  [31:24] xflags
 //     word B: [7:0] yA  [15:8] yB  [19:16] cA                [23:20] cB  [31:24] yflags
@@ -55,6 +56,7 @@ static constexpr int kConstSlots = 64;
 //                       bits to clear (compression flags), cB = 0: 48-byte field, 1: 32-byte field)
 //                  bit2 XLANE  (read the slot column of lane ^ mask)
 //                  bit3 SIMPLE (operand is exactly one shared-memory slot, coefficient +1: fast path)
+//                  bits 4..6: pre-decoded fast mode for shared-memory slots: 1 = -A, 2 = A+B, 3 = A-B, 4 = -A-B
 enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3, OP_INV = 4 };
 enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8 };
 static constexpr uint32_t H_BAR = 1u << 25;
@@ -214,6 +216,18 @@ FPC_DEV void load_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask)
         load_near(r, c, w & 0xFF);
         return;
     }
+    const uint32_t fast = (w >> 28) & 0x7;
+    if (fast) {  // pre-decoded modes on shared-memory slots
+        load_near(r, c, w & 0xFF);
+        if (fast == 1) { fpc::neg_raw(r, r); return; }
+        uint32_t u[12];
+        load_near(u, c, (w >> 8) & 0xFF);
+        if (fast == 2) { (void)fpc::add12(r, r, u); return; }
+        if (fast == 3) { fpc::neg_raw(u, u); (void)fpc::add12(r, r, u); return; }
+        (void)fpc::add12(r, r, u);   // fast == 4: -A - B = 2p - (A + B)
+        fpc::neg_raw2(r, r);
+        return;
+    }
     const uint32_t a = w & 0xFF, b = (w >> 8) & 0xFF, flags = w >> 24;
     const int ca = sext4(w >> 16), cb = sext4(w >> 20);
     if (flags & F_GLOBAL) {
@@ -275,6 +289,10 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
             fpc::acc_mac(A, x, y);
         }
         fpc::acc_redc(A, r);
+        if (!(hdr & H_PADCONST)) {  // common integer factor of all products, applied once to the reduced sum
+            const uint32_t ps = aux >> 24;
+            if (ps > 1) scale_raw(r, (int)ps);
+        }
     } else {
         fpc::zero12(r);
     }

@@ -4,9 +4,10 @@
 
 namespace vm {
 
-__device__ __forceinline__ void wait_progress(const volatile uint32_t* progress, uint32_t w, uint32_t need) {
+__device__ __forceinline__ void wait_progress(const volatile uint32_t* progress, uint32_t w, uint32_t need, uint32_t sleep_ns) {
     if (need == 0) return;
     while (progress[w] < need) {
+        if (sleep_ns) __nanosleep(sleep_ns);  // back off: a spinning warp steals issue slots and LDS bandwidth
     }
 }
 
@@ -48,12 +49,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
             const uint32_t hdr = __shfl_sync(0xffffffffu, cur, 0);
             const uint32_t aux = __shfl_sync(0xffffffffu, cur, 1);
             if (hdr & H_BAR) {  // this record carries progress requirements
-                const uint32_t w01 = __shfl_sync(0xffffffffu, cur, 27), w23 = __shfl_sync(0xffffffffu, cur, 29);
-                const uint32_t w45 = __shfl_sync(0xffffffffu, cur, 30), w67 = __shfl_sync(0xffffffffu, cur, 31);
-                wait_progress(progress, 0, w01 & 0xFFFF); wait_progress(progress, 1, w01 >> 16);
-                wait_progress(progress, 2, w23 & 0xFFFF); wait_progress(progress, 3, w23 >> 16);
-                wait_progress(progress, 4, w45 & 0xFFFF); wait_progress(progress, 5, w45 >> 16);
-                wait_progress(progress, 6, w67 & 0xFFFF); wait_progress(progress, 7, w67 >> 16);
+                const uint32_t q0 = __shfl_sync(0xffffffffu, cur, 27), q1 = __shfl_sync(0xffffffffu, cur, 29);
+                const uint32_t q2 = __shfl_sync(0xffffffffu, cur, 30), q3 = __shfl_sync(0xffffffffu, cur, 31);
+                if (WARPS <= 8) {  // eight 16-bit fields
+                    wait_progress(progress, 0, q0 & 0xFFFF, L.pad); wait_progress(progress, 1, q0 >> 16, L.pad);
+                    wait_progress(progress, 2, q1 & 0xFFFF, L.pad); wait_progress(progress, 3, q1 >> 16, L.pad);
+                    wait_progress(progress, 4, q2 & 0xFFFF, L.pad); wait_progress(progress, 5, q2 >> 16, L.pad);
+                    wait_progress(progress, 6, q3 & 0xFFFF, L.pad); wait_progress(progress, 7, q3 >> 16, L.pad);
+                } else {           // ten 12-bit fields packed little-endian over the four words
+                    const uint64_t lo = ((uint64_t)q1 << 32) | q0, hi = ((uint64_t)q3 << 32) | q2;
+#pragma unroll
+                    for (int k = 0; k < WARPS && k < 10; ++k) {
+                        const int bit = 12 * k;
+                        uint32_t need;
+                        if (bit + 12 <= 64) need = (uint32_t)(lo >> bit) & 0xFFF;
+                        else if (bit >= 64) need = (uint32_t)(hi >> (bit - 64)) & 0xFFF;
+                        else need = (uint32_t)((lo >> bit) | (hi << (64 - bit))) & 0xFFF;
+                        wait_progress(progress, k, need, L.pad);
+                    }
+                }
                 __threadfence_block();
                 __syncwarp();
             }
@@ -71,5 +85,6 @@ template __global__ void vm_kernel<2, 8>(const Launch);
 template __global__ void vm_kernel<4, 4>(const Launch);
 template __global__ void vm_kernel<6, 2>(const Launch);
 template __global__ void vm_kernel<8, 2>(const Launch);
+template __global__ void vm_kernel<10, 2>(const Launch);
 
 }  // namespace vm

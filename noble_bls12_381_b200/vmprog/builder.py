@@ -33,7 +33,7 @@ H_BAR, H_DSTG, H_DSTWORD, H_DSTBATCH, H_PADCONST, H_POST_ISZERO, H_POST_GTHALF =
 REC_WORDS = 32
 MAX_TERMS = 12
 MAX_SUM_BOUND = 80.0  # sum of |x|*|y| bounds in units of p^2 that fits the 768-bit accumulator
-MAX_K = 8.0  # result bound (units of p) that `correct` can bring back to [0,p)
+MAX_K = 9.5  # result bound (units of p): must stay below 2^384 / p = 9.84; `correct` handles up to 4 rounds
 
 
 # ------------------------------------------------------------------------------------------ values
@@ -177,6 +177,7 @@ class Op:
     sel: list = field(default_factory=list)  # [flag, a, b] Operands for kind == "sel"
     bit: tuple | None = None  # (buf, off16, nbytes, bitindex) for kind == "bit"
     dst_word: bool = False  # int32 status store
+    post_scale: int = 1  # the reduced sum of products is multiplied by this small factor
     per_batch: bool = False  # global store by lane 0 at index item/32
     pad_const: Val | None = None  # padding lanes (item >= n_items) produce this constant instead
     after: list = field(default_factory=list)  # extra ordering deps (Ops)
@@ -412,13 +413,33 @@ class Builder:
         if not q.terms and q.lin.is_zero():
             q = Quad([], Lin.of(self.const_raw(0)))
         # product terms: make each side a valid operand
-        terms = []
+        # normalise every product to k * x' * y' with primitive operands, then pull the common integer factor g of
+        # all products out of the sum: it is applied ONCE to the reduced result (post-scale) instead of to an
+        # operand of every term
+        import math
+        norm = []
         for k, x, y in q.terms:
             x, y = self.lin_operand(x), self.lin_operand(y)
+            gx = math.gcd(*[abs(c) for c in x.t.values()])
+            gy = math.gcd(*[abs(c) for c in y.t.values()])
+            x = Lin({v: c // gx for v, c in x.t.items()})
+            y = Lin({v: c // gy for v, c in y.t.items()})
+            norm.append((k * gx * gy, x, y))
+        g = 0
+        for k, _, _ in norm:
+            g = math.gcd(g, abs(k))
+        post = 1
+        for cand in (4, 3, 2):
+            if g and g % cand == 0:
+                post = cand
+                break
+        terms = []
+        for k, x, y in norm:
+            k //= post
             if k < 0:
                 x, k = -x, -k
             while k > 0:
-                # fold as much of the integer factor as the 4-bit operand coefficients allow
+                # fold as much of the remaining integer factor as the 4-bit operand coefficients allow
                 fx = 4 // max(abs(c) for c in x.t.values())
                 fy = 4 // max(abs(c) for c in y.t.values())
                 best = None
@@ -442,11 +463,11 @@ class Builder:
             while pending_terms and len(cur_t) < MAX_TERMS:
                 x, y = pending_terms[0]
                 b = x.bound() * y.bound()
-                if sumb + b > MAX_SUM_BOUND or (sumb + b) * P_OVER_R + 1 + kb > MAX_K - 0.01:
+                if sumb + b > MAX_SUM_BOUND or post * ((sumb + b) * P_OVER_R + 1) + kb > MAX_K - 0.01:
                     break
                 cur_t.append(pending_terms.pop(0))
                 sumb += b
-            base = (sumb * P_OVER_R + 1) if cur_t else 0.0
+            base = post * (sumb * P_OVER_R + 1) if cur_t else 0.0
             while pending_epi and len(cur_e) < 2:
                 b = pending_epi[0].bound()
                 if base + kb + b > MAX_K - 0.01:
@@ -456,8 +477,8 @@ class Builder:
             assert cur_t or cur_e, "cannot make progress materialising expression"
             done = not pending_terms and not pending_epi
             if done and not partial:
-                return self._emit(cur_t, cur_e, base + kb)
-            partial.append(self._emit(cur_t, cur_e, base + kb))
+                return self._emit(cur_t, cur_e, base + kb, post)
+            partial.append(self._emit(cur_t, cur_e, base + kb, post))
             if done:
                 break
             # fold partial results into the epilogue queue
@@ -486,7 +507,7 @@ class Builder:
                     i += 1
         return chunks
 
-    def _emit(self, lin_terms, lin_epi, k_bound) -> Val:
+    def _emit(self, lin_terms, lin_epi, k_bound, post_scale=1) -> Val:
         terms = [(self._operand(x), self._operand(y)) for x, y in lin_terms]
         epi = [self._operand(z) for z in lin_epi]
         # operands with negative coefficients are bounded INCLUSIVELY (p - 0 = p), so require 2^ncorr > k
@@ -499,8 +520,11 @@ class Builder:
             ncorr = 0
             while (1 << ncorr) < k - 1e-9:
                 ncorr += 1
-        assert ncorr <= 3, k
-        return self._new_op(terms, epi, ncorr).out
+        assert ncorr <= 4, k
+        op = self._new_op(terms, epi, ncorr)
+        if terms:
+            op.post_scale = post_scale
+        return op.out
 
     # ------------------------------------------------------------------------------------------
     # reference evaluation of the SSA program on plain integers (no scheduling/slots): used by tests
@@ -539,7 +563,7 @@ class Builder:
                     acc = 0
                     for x, y in op.terms:
                         acc += ev_operand(x, lane, op.xmask) * ev_operand(y, lane, op.xmask)
-                    r = acc * rinv % P if op.terms else 0
+                    r = acc * rinv % P * op.post_scale if op.terms else 0
                     for e in op.epi:
                         r += ev_operand(e, lane, op.xmask)
                 r %= P
@@ -778,15 +802,29 @@ class Builder:
         a = idx(o.a)
         b = idx(o.b) if o.b is not None else 0
         flags = o.flags
-        if flags == 0 and o.ca == 1 and (o.b is None or o.cb == 0) and a < self.nslots:
-            flags |= F_SIMPLE
+        cb = o.cb if o.b is not None else 0
+        near = a < self.nslots and (cb == 0 or b < self.nslots)
+        if flags == 0 and near:
+            if (o.ca, cb) == (1, 0):
+                flags |= F_SIMPLE
+            elif (o.ca, cb) == (-1, 0):
+                flags |= 1 << 4
+            elif (o.ca, cb) == (1, 1):
+                flags |= 2 << 4
+            elif (o.ca, cb) == (1, -1):
+                flags |= 3 << 4
+            elif (o.ca, cb) == (-1, 1):
+                a, b = b, a
+                flags |= 3 << 4
+            elif (o.ca, cb) == (-1, -1):
+                flags |= 4 << 4
         return a | (b << 8) | ((o.ca & 0xF) << 16) | ((o.cb & 0xF) << 20) | (flags << 24)
 
     def encode(self):
         """Returns (prog: bytes [W][nrec][32 words], nrec).  Words 27, 29, 30, 31 hold eight 16-bit progress
         requirements (warps 0..7)."""
         W = self.warps
-        assert W <= 8
+        assert W <= 10
         streams = []
         for w in range(W):
             recs = []
@@ -811,8 +849,11 @@ class Builder:
                     if op.per_batch:
                         hdr |= H_DSTBATCH
                 if op.pad_const is not None:
+                    assert op.post_scale == 1
                     hdr |= H_PADCONST
                     aux |= op.pad_const.cidx << 24
+                elif op.post_scale > 1:
+                    aux |= op.post_scale << 24
                 words[0], words[1] = hdr, aux
                 for t, (x, y) in enumerate(op.terms):
                     words[2 + 2 * t] = self._enc_operand(x)
@@ -826,14 +867,22 @@ class Builder:
                 elif op.kind == "bit":
                     buf, off16, nbytes, bitindex = op.bit
                     words[2], words[3], words[4] = buf | (off16 << 8), bitindex, nbytes
-                wt = self.waits[i] + [0] * (8 - W)
-                assert max(wt) < 65536
+                wt = self.waits[i]
                 if any(wt):
                     words[0] |= H_BAR  # "has waits"
-                words[27] = wt[0] | (wt[1] << 16)
-                words[29] = wt[2] | (wt[3] << 16)
-                words[30] = wt[4] | (wt[5] << 16)
-                words[31] = wt[6] | (wt[7] << 16)
+                if W <= 8:  # eight 16-bit fields
+                    wt = wt + [0] * (8 - W)
+                    assert max(wt) < 65536
+                    words[27] = wt[0] | (wt[1] << 16)
+                    words[29] = wt[2] | (wt[3] << 16)
+                    words[30] = wt[4] | (wt[5] << 16)
+                    words[31] = wt[6] | (wt[7] << 16)
+                else:  # ten 12-bit fields, little-endian over words 27, 29, 30, 31
+                    assert max(wt) < 4096
+                    big = 0
+                    for k, v_ in enumerate(wt):
+                        big |= v_ << (12 * k)
+                    words[27], words[29], words[30], words[31] = [(big >> (32 * j)) & 0xFFFFFFFF for j in range(4)]
                 recs.append(words)
             streams.append(recs)
         nrec = max(len(s_) for s_ in streams)
