@@ -36,8 +36,8 @@ struct State {
     static constexpr int kStages = 10;
     uint8_t* d_stage[kStages] = {};
     size_t stage_bytes[kStages] = {};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     double last_ms = 0.0;
     std::atomic<uint64_t> launches{0};
     std::string program_dir;
@@ -362,8 +362,11 @@ int bls381_init(int device, const char* program_dir) {
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g.ev0));
     CUDA_TRY(cudaEventCreate(&g.ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
     g.inited = true;
     return BLS381_OK;
 }
@@ -387,7 +390,10 @@ int bls381_shutdown(void) {
     }
     cudaEventDestroy(g.ev0);
     cudaEventDestroy(g.ev1);
+    cudaEventDestroy(g.ev_fork);
+    cudaEventDestroy(g.ev_join);
     cudaStreamDestroy(g.stream);
+    cudaStreamDestroy(g.stream2);
     g.inited = false;
     return BLS381_OK;
 }
@@ -571,17 +577,22 @@ static int verify_partial(const uint8_t* sig96, const uint8_t* msgs, const uint6
     }
     if (sig96) CUDA_TRY(cudaMemcpyAsync(g.d_stage[7] + n * 48, sig96, 96, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(g.ev0, s));
+    if (sig96) {
+        // normP2(signature) (index.ts:799) and the pairing(G1.negate(), sig) term (index.ts:814): a single-item,
+        // latency-bound launch (no far slots) -> runs on a second stream underneath the bulk stages
+        CUDA_TRY(cudaEventRecord(g.ev_fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(g.stream2, g.ev_fork, 0));
+        if ((rc = run3("g2_decompress", g.d_stage[7] + n * 48, 96, d_g2 + n * 192, 192, d_st + n, 1, g.stream2))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_g1 + n * 96, kNegG1, 96, cudaMemcpyHostToDevice, g.stream2));
+        CUDA_TRY(cudaEventRecord(g.ev_join, g.stream2));
+    }
     if (n) {
         // publicKeys.map(normP1)  (index.ts:801)
         if ((rc = run3("g1_decompress", g.d_stage[7], 48, d_g1, 96, d_st, n, s))) return rc;
         // messages.map(normP2Hash)  (index.ts:800)
         if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, d_g2, s))) return rc;
     }
-    if (sig96) {
-        // normP2(signature)  (index.ts:799) and the pairing(G1.negate(), sig) term (index.ts:814)
-        if ((rc = run3("g2_decompress", g.d_stage[7] + n * 48, 96, d_g2 + n * 192, 192, d_st + n, 1, s))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_g1 + n * 96, kNegG1, 96, cudaMemcpyHostToDevice, s));
-    }
+    if (sig96) CUDA_TRY(cudaStreamWaitEvent(s, g.ev_join, 0));
     // product of the Miller loops (+ one final exponentiation)  (index.ts:812-816)
     if ((rc = miller_product_dev(d_g1, d_g2, np, with_final_exp, g.d_stage[8], s))) return rc;
     CUDA_TRY(cudaEventRecord(g.ev1, s));
