@@ -20,7 +20,7 @@
 namespace {
 
 struct Program {
-    uint32_t warps = 0, nrec = 0, nconst = 0, nslots = 0, nfar = 0;
+    uint32_t warps = 0, nrec = 0, nconst = 0, nslots = 0, nfar = 0, staged_mask = 0;
     uint32_t* d_prog = nullptr;
     uint32_t* d_consts = nullptr;
 };
@@ -43,6 +43,7 @@ struct State {
     std::string program_dir;
     int force_ctas = 0;  // tuning override (env BLS381_B200_CTAS)
     int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
+    int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
 };
 
 State g;
@@ -69,7 +70,7 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     memcpy(h, img, 32);
     if (h[0] != kMagic || h[1] != 1) return fail(BLS381_EPROGRAM, "bad program magic/version: " + name);
     Program p;
-    p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6];
+    p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6]; p.staged_mask = h[7];
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
     if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
@@ -129,7 +130,10 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     int rc = get_program(name, &p);
     if (rc) return rc;
     const uint32_t nbatch = (uint32_t)((n + 31) / 32);
-    const size_t smem_est = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 1024;
+    size_t stage_est = 0;
+    for (int i = 0; i < nbuf; ++i)
+        if ((p->staged_mask >> i & 1) && strides[i]) stage_est += 32u * strides[i];
+    const size_t smem_est = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 16 + std::min<size_t>(stage_est, 20480) + 1024;
     const int max_ctas = p->warps == 2 ? 8 : (p->warps == 4 ? 4 : 2);
     int ctas_per_sm = std::max(1, std::min(max_ctas, (int)(232448 / smem_est)));
     if (g.force_ctas > 0) ctas_per_sm = std::min(ctas_per_sm, g.force_ctas);
@@ -157,7 +161,19 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
         L.buf[i].base = bufs[i];
         L.buf[i].stride = strides[i];
     }
-    const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64;  // slots + constants + progress counters
+    // TMA staging plan: every wire-format input buffer the program reads, if its pointer and stride allow 16-byte
+    // aligned bulk copies (otherwise that buffer is read directly from global memory)
+    uint32_t stage_bytes = 0;
+    for (int i = 0; i < vm::kMaxBuffers; ++i) {
+        L.stage_off[i] = vm::kNoStage;
+        if (!g.no_tma && i < nbuf && (p->staged_mask >> i & 1) && bufs[i] && strides[i] && strides[i] % 16 == 0 &&
+            reinterpret_cast<uintptr_t>(bufs[i]) % 16 == 0 && stage_bytes + 32u * strides[i] <= 20480) {
+            L.stage_off[i] = stage_bytes;
+            stage_bytes += 32u * strides[i];
+        }
+    }
+    L.stage_bytes = stage_bytes;
+    const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 16 + stage_bytes;  // slots + constants + progress + mbarrier + staging
     g.launches.fetch_add(1);
     if (p->warps == 2) return launch_w<2, 8>(L, grid, smem, s);
     if (p->warps == 4) return launch_w<4, 4>(L, grid, smem, s);
@@ -361,6 +377,7 @@ int bls381_init(int device, const char* program_dir) {
     }
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
+    if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g.ev0));

@@ -84,7 +84,13 @@ struct Launch {
     uint32_t pad;
     uint32_t* far;          // [ctas][nfar][kSlotWords]
     Buffer buf[kMaxBuffers];
+    // TMA staging: wire-format input buffers whose 32-item batch record block (32 x stride bytes, contiguous) is
+    // bulk-copied into shared memory at the start of every batch; kNoStage = read directly from global memory
+    uint32_t stage_off[kMaxBuffers];   // byte offset inside the staging area
+    uint32_t stage_bytes;              // total staging bytes (multiple of 16)
+    uint32_t pad2;
 };
+static constexpr uint32_t kNoStage = 0xFFFFFFFFu;
 
 // ---- per-lane execution context -------------------------------------------------------------------
 struct Ctx {
@@ -97,7 +103,17 @@ struct Ctx {
     uint32_t batch;          // index of the 32-item batch being processed
     bool store_ok;           // lane < n_items
     const Buffer* buf;
+    const uint8_t* stage;    // shared-memory staging area filled by TMA (nullptr in the CPU emulation)
+    const uint32_t* stage_off;
 };
+
+// start of this lane's record in input buffer `bufid` (TMA-staged copy in shared memory when available)
+FPC_DEV const uint8_t* wire_record(const Ctx& c, uint32_t bufid) {
+    const Buffer& b = c.buf[bufid];
+    if (c.stage != nullptr && c.stage_off[bufid] != kNoStage && c.store_ok)
+        return c.stage + c.stage_off[bufid] + (size_t)c.lane * b.stride;
+    return b.base + (size_t)c.item * b.stride;
+}
 
 FPC_DEV uint32_t bswap32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -150,8 +166,7 @@ FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
 
 // wire format: big-endian field (48 or 32 bytes) at byte offset 16*off16 -> 12 little-endian limbs
 FPC_DEV void load_wire(uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t off16, uint32_t clear_top, uint32_t short32) {
-    const Buffer& b = c.buf[bufid];
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(b.base + (size_t)c.item * b.stride + off16 * 16u);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(wire_record(c, bufid) + off16 * 16u);
     if (short32) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) r[k] = bswap32(p[7 - k]);
@@ -274,8 +289,7 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
         fpc::fp_inv_mont(r, xin);
     } else if (op == OP_BIT) {
         const uint32_t w2 = W(2), bit = W(3), nbytes = W(4);
-        const Buffer& bf = c.buf[w2 & 0xFF];
-        const uint8_t* p = bf.base + (size_t)c.item * bf.stride + ((w2 >> 8) & 0xFF) * 16u;
+        const uint8_t* p = wire_record(c, w2 & 0xFF) + ((w2 >> 8) & 0xFF) * 16u;
         const uint32_t byte = p[nbytes - 1 - (bit >> 3)];
         fpc::zero12(r);
         r[0] = (byte >> (bit & 7)) & 1u;

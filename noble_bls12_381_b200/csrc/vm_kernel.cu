@@ -20,6 +20,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     uint32_t* slots = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* sconst = slots + (size_t)L.nslots * kSlotWords;
     volatile uint32_t* progress = sconst + (size_t)L.nconst * 12;  // [16]
+    // TMA staging area + its mbarrier (16-byte aligned: slots and constants are multiples of 16 bytes)
+    uint8_t* stage = reinterpret_cast<uint8_t*>(sconst + (size_t)L.nconst * 12 + 16 + 4);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(sconst + (size_t)L.nconst * 12 + 16);
+    if (L.stage_bytes && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase = 0;
     for (uint32_t i = threadIdx.x; i < L.nconst * 12; i += blockDim.x) sconst[i] = L.consts[i];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,6 +41,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     c.nslots = L.nslots;
     c.lane = lane;
     c.buf = L.buf;
+    c.stage = L.stage_bytes ? stage : nullptr;
+    c.stage_off = L.stage_off;
 
     for (uint32_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const uint32_t item = batch * 32 + lane;
@@ -41,6 +51,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
         c.batch = batch;
         __syncthreads();  // previous batch fully retired (and constants visible)
         if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+        if (L.stage_bytes) {
+            // stage this batch's wire-format inputs: one elected thread issues 1-D bulk copies (TMA) of the batch's
+            // contiguous record block of every staged buffer; everybody then waits on the mbarrier phase
+            if (threadIdx.x == 0) {
+                const uint32_t items = min(32u, L.n_items - batch * 32u);
+                uint32_t total = 0;
+#pragma unroll
+                for (int b = 0; b < kMaxBuffers; ++b)
+                    if (L.stage_off[b] != kNoStage) total += items * L.buf[b].stride;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
+#pragma unroll
+                for (int b = 0; b < kMaxBuffers; ++b) {
+                    if (L.stage_off[b] == kNoStage) continue;
+                    const uint32_t bytes = items * L.buf[b].stride;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + L.stage_off[b]);
+                    const uint8_t* src = L.buf[b].base + (size_t)batch * 32u * L.buf[b].stride;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+                }
+            }
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+            } while (!done);
+            phase ^= 1;
+        }
         __syncthreads();
         uint32_t next = stream[lane];
         for (uint32_t r = 0; r < L.nrec; ++r) {

@@ -14,12 +14,20 @@ from . import curves, tower
 MAGIC = 0x4D563242  # 'B2VM'
 VERSION = 1
 DEFAULT_WARPS = 8
-DEFAULT_SLOTS = 72
+DEFAULT_SLOTS = 66  # + up to 9 KB of TMA input staging per CTA, two CTAs per SM
 
 
 def image(b) -> bytes:
     prog, nrec = b.encode()
-    hdr = struct.pack("<8I", MAGIC, VERSION, b.warps, nrec, len(b.consts), b.nslots, b.nfar, 0)
+    staged = 0  # bit mask of the wire-format input buffers (TMA-staged into shared memory per batch)
+    for op in b.ops:
+        for x, y in op.terms:
+            for o in (x, y):
+                if o.flags & 2:
+                    staged |= 1 << o.gl[0]
+        if op.kind == "bit":
+            staged |= 1 << op.bit[0]
+    hdr = struct.pack("<8I", MAGIC, VERSION, b.warps, nrec, len(b.consts), b.nslots, b.nfar, staged)
     return hdr + b.const_table() + prog
 
 

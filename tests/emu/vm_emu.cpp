@@ -75,6 +75,7 @@ int vm_emu_run(const uint32_t* prog, int warps, int nrec, const uint32_t* consts
                 c.item = c.store_ok ? item : (uint32_t)n_items - 1;
                 c.buf = buf;
                 c.batch = batch;
+                c.stage = nullptr; c.stage_off = nullptr;
                 vm::exec_record(c, rec[0], rec[1], [&](uint32_t i) { return rec[i]; });
             }
             ++pc[w];
