@@ -124,6 +124,9 @@ int bls381_g2_validate_batch(const uint8_t* g2_affine, size_t n, int32_t* status
  *   scalars32: 0 < k <= r big-endian; out192 affine; flags[i] bit1 = result is the point at infinity          */
 int bls381_g2_scalar_mul_batch(const uint8_t* g2_affine, const uint8_t* scalars32, size_t n, uint8_t* out192,
                                int32_t* flags);
+/* PointG1#multiply / multiplyUnsafe (math.ts:1048-1078): same for G1 (96-byte affine points).                  */
+int bls381_g1_scalar_mul_batch(const uint8_t* g1_affine, const uint8_t* scalars32, size_t n, uint8_t* out96,
+                               int32_t* flags);
 /* prod_i f_i in Fp12 (+ optional finalExponentiate): combines the per-GPU partial products of a sharded
  * verifyBatch after the all-gather (index.ts:815-816).  in: n x 576 B, out: 576 B.                          */
 int bls381_fp12_product(const uint8_t* in_fp12, size_t n, int with_final_exp, uint8_t* out_fp12);

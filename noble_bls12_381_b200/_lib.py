@@ -43,6 +43,7 @@ def _load():
     lib.bls381_fp12_product.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
     lib.bls381_g1_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_g2_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_g1_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_g2_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_verify_batch_partial.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_verify_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
@@ -56,7 +57,7 @@ EXPORTS = [
     "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms",
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
     "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
-    "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_verify_batch_partial",
+    "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_g1_scalar_mul_batch", "bls381_verify_batch_partial",
 ]
 
 
@@ -170,6 +171,12 @@ class Engine:
         out = ctypes.create_string_buffer(192 * n)
         fl = (ctypes.c_int32 * n)()
         self._check(self.lib.bls381_g2_scalar_mul_batch(g2, scalars32, n, out, fl))
+        return out.raw, list(fl)
+
+    def g1_scalar_mul_batch(self, g1: bytes, scalars32: bytes, n: int):
+        out = ctypes.create_string_buffer(96 * n)
+        fl = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g1_scalar_mul_batch(g1, scalars32, n, out, fl))
         return out.raw, list(fl)
 
     def fp12_product(self, f12: bytes, n: int, with_final_exp: bool = False) -> bytes:

@@ -162,6 +162,32 @@ class PointG1:
     def toHex(self, isCompressed=False) -> str:
         return self.toRawBytes(isCompressed).hex()
 
+    # group law on the device (math.ts:974-1078); results are canonical affine points
+    def add(self, o: "PointG1") -> "PointG1":
+        if self.inf:
+            return o
+        if o.inf:
+            return self
+        out, _ = _eng().aggregate_g1(self.toRawBytes(True) + o.toRawBytes(True), 2)
+        return PointG1.fromHex(out)
+
+    def subtract(self, o: "PointG1") -> "PointG1":
+        return self.add(o.negate())
+
+    def double(self) -> "PointG1":
+        return self.add(self)
+
+    def multiply(self, scalar: int) -> "PointG1":
+        if not isinstance(scalar, int) or scalar <= 0 or scalar > R_ORDER:
+            raise ValueError(f"Point#multiply: invalid scalar, expected positive integer < CURVE.r. Got: {scalar}")
+        if self.inf:
+            return self
+        out, fl = _eng().g1_scalar_mul_batch(self.wire(), scalar.to_bytes(32, "big"), 1)
+        return PointG1.ZERO if fl[0] & 2 else PointG1(int.from_bytes(out[:48], "big"), int.from_bytes(out[48:], "big"))
+
+    multiplyUnsafe = multiply
+    multiplyPrecomputed = multiply
+
     @staticmethod
     def fromPrivateKey(pk) -> "PointG1":  # index.ts:351-353; key generation is host-side
         k = normalizePrivKey(pk)
@@ -272,6 +298,22 @@ class PointG2:
             return self
         out, fl = _eng().g2_scalar_mul_batch(self.wire(), scalar.to_bytes(32, "big"), 1)
         return PointG2.ZERO if fl[0] & 2 else PointG2._from_wire(out)
+
+    def add(self, o: "PointG2") -> "PointG2":
+        if self.inf:
+            return o
+        if o.inf:
+            return self
+        out, _ = _eng().aggregate_g2(self.toSignature() + o.toSignature(), 2)
+        return PointG2.fromSignature(out)
+
+    def subtract(self, o: "PointG2") -> "PointG2":
+        return self.add(o.negate())
+
+    def double(self) -> "PointG2":
+        return self.add(self)
+
+    multiplyUnsafe = multiply
 
     def toSignature(self) -> bytes:  # index.ts:586-598
         if self.inf:

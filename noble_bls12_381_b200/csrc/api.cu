@@ -768,23 +768,33 @@ int bls381_g2_validate_batch(const uint8_t* g2_affine, size_t n, int32_t* status
     return validate_host(true, g2_affine, n, status);
 }
 
-int bls381_g2_scalar_mul_batch(const uint8_t* g2_affine, const uint8_t* scalars32, size_t n, uint8_t* out192, int32_t* flags) {
-    std::lock_guard<std::mutex> lk(g_mu);
+static int scalar_mul_host(bool g2, const uint8_t* pts, const uint8_t* scalars32, size_t n, uint8_t* out, int32_t* flags) {
     if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
-    if (!g2_affine || !scalars32 || !out192 || !flags) return fail(BLS381_EINVAL, "null argument");
+    if (!pts || !scalars32 || !out || !flags) return fail(BLS381_EINVAL, "null argument");
     if (n == 0) return BLS381_OK;
+    const uint32_t ab = g2 ? 192 : 96;
     int rc;
-    if ((rc = stage(0, n * 192)) || (rc = stage(7, n * 32)) || (rc = stage(2, n * 192)) || (rc = stage(6, n * 4))) return rc;
+    if ((rc = stage(0, n * ab)) || (rc = stage(7, n * 32)) || (rc = stage(2, n * ab)) || (rc = stage(6, n * 4))) return rc;
     cudaStream_t s = g.stream;
-    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], g2_affine, n * 192, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], pts, n * ab, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], scalars32, n * 32, cudaMemcpyHostToDevice, s));
     uint8_t* bufs[6] = {g.d_stage[0], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
-    uint32_t strides[6] = {192, 32, 192, 0, 0, 4};
-    if ((rc = vm_run("g2_scalar_mul", bufs, strides, 6, n, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, s));
+    uint32_t strides[6] = {ab, 32, ab, 0, 0, 4};
+    if ((rc = vm_run(g2 ? "g2_scalar_mul" : "g1_scalar_mul", bufs, strides, 6, n, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[2], n * ab, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(flags, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return BLS381_OK;
+}
+
+int bls381_g2_scalar_mul_batch(const uint8_t* g2_affine, const uint8_t* scalars32, size_t n, uint8_t* out192, int32_t* flags) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return scalar_mul_host(true, g2_affine, scalars32, n, out192, flags);
+}
+
+int bls381_g1_scalar_mul_batch(const uint8_t* g1_affine, const uint8_t* scalars32, size_t n, uint8_t* out96, int32_t* flags) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return scalar_mul_host(false, g1_affine, scalars32, n, out96, flags);
 }
 
 int bls381_imad_peak(double* imad_per_second) {

@@ -34,7 +34,7 @@ def image(b) -> bytes:
 # ingest programs are serial Fp2 chains: fewer warps per CTA, more CTAs per SM
 INGEST_WARPS = {"g1_decompress": 2, "g2_decompress": 4, "hash_to_g2": 4, "sign": 4, "g1_sum_affine": 4, "g1_sum_proj": 4,
                 "g2_sum_affine": 4, "g2_sum_proj": 4, "g1_compress": 2, "g2_compress": 2, "g1_validate": 2, "g2_validate": 4,
-                "g2_scalar_mul": 4}
+                "g2_scalar_mul": 4, "g1_scalar_mul": 4}
 ALL_PROGRAMS = dict(tower.PROGRAMS)
 ALL_PROGRAMS.update(curves.PROGRAMS)
 

@@ -781,7 +781,25 @@ def build_g2_scalar_mul(warps=4) -> Builder:
     return b
 
 
+def build_g1_scalar_mul(warps=4) -> Builder:
+    """ProjectivePoint#multiply / multiplyUnsafe on G1 (math.ts:1048-1078): buffer 0 affine point, buffer 1 32-byte
+    scalar -> buffer 2 affine result, buffer 5 flag word (bit1 = point at infinity)."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    one = Lin.of(b.mat(t.fp_const(1)))
+    p = (Lin.of(b.inp(BUF_IN, 0)), Lin.of(b.inp(BUF_IN, 1)), one)
+    s = ig.G1.mul_secret(p, R_ORDER.bit_length(), lambda i: b.bit(BUF_AUX, 0, 32, i))
+    is_inf = b.is_zero(s[2])
+    x, y = ig.g1_to_affine(s)
+    b.out(x, BUF_OUT, 0)
+    b.out(y, BUF_OUT, 1)
+    b.out_word(b.select(is_inf, Lin.of(b.const_raw(2)), Lin.of(b.const_raw(0))), BUF_STATUS)
+    return b
+
+
 PROGRAMS.update({
+    "g1_scalar_mul": build_g1_scalar_mul,
     "g1_validate": lambda w: _build_validate("g1", w),
     "g2_validate": lambda w: _build_validate("g2", w),
     "g2_scalar_mul": build_g2_scalar_mul,

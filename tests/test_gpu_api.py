@@ -130,3 +130,55 @@ def test_dst_label_is_forwarded(bls, vectors):
     finally:
         bls.utils.setDSTLabel(old)
     assert bls.sign(vectors[3][1], vectors[3][0].rjust(64, "0")).hex() == vectors[3][2]
+
+
+def test_point_group_law_and_zkcrypto_multiples(bls):
+    """deterministic.test.ts:49-113: i*G by repeated addition and by all multipliers equals the zkcrypto encodings;
+    point.test.ts doubling identities."""
+    g1c = open(os.path.join(GOLDEN, "zkcrypto_g1_compressed.dat"), "rb").read()
+    g2c = open(os.path.join(GOLDEN, "zkcrypto_g2_compressed.dat"), "rb").read()
+    p1, p2 = bls.PointG1.ZERO, bls.PointG2.ZERO
+    for i in range(6):
+        assert p1.toRawBytes(True) == g1c[48 * i : 48 * i + 48]
+        assert p2.toRawBytes(True) == g2c[96 * i : 96 * i + 96]
+        p1, p2 = p1.add(bls.PointG1.BASE), p2.add(bls.PointG2.BASE)
+    for i in (1, 2, 3, 17, 999):
+        assert bls.PointG1.BASE.multiply(i).toRawBytes(True) == g1c[48 * i : 48 * i + 48]
+        assert bls.PointG1.BASE.multiplyUnsafe(i).toRawBytes(True) == g1c[48 * i : 48 * i + 48]
+        assert bls.PointG2.BASE.multiply(i).toRawBytes(True) == g2c[96 * i : 96 * i + 96]
+    G, H = bls.PointG1.BASE, bls.PointG2.BASE
+    assert G.double().equals(G.add(G)) and G.double().equals(G.multiply(2))
+    assert G.add(G.negate()).isZero() and H.subtract(H).isZero()
+    assert G.multiply(bls.R_ORDER).isZero() and H.multiply(bls.R_ORDER).isZero()
+    assert G.multiply(5).subtract(G.multiply(2)).equals(G.multiply(3))
+
+
+def test_full_size_properties(bls):
+    """Size-independent properties at BASELINE.json's sizes (config 3: 262 144 signatures; config 4 slice):
+    sign -> aggregate -> verifyBatch round trip must be true, one flipped message byte must make it false."""
+    import hashlib
+    from noble_bls12_381_b200 import synth
+    n = 262144
+    eng = bls._eng()
+    dst = bls._dst()
+    g1, _ = synth.multiples_wire(n)  # public keys (i+1)*G1 for secret keys i+1
+    pks = []
+    for i in range(n):
+        x = int.from_bytes(g1[96 * i : 96 * i + 48], "big")
+        y = int.from_bytes(g1[96 * i + 48 : 96 * i + 96], "big")
+        pks.append((x + ((y * 2) // bls.P) * (1 << 381) + (1 << 383)).to_bytes(48, "big"))
+    msgs = [hashlib.sha256(i.to_bytes(8, "big")).digest() for i in range(n)]
+    sks = b"".join((i + 1).to_bytes(32, "big") for i in range(n))
+    sigs = eng.sign_batch(sks, msgs, dst)
+    agg, st = eng.aggregate_g2(sigs, n)
+    assert all(s == 0 for s in st)
+    v, st = eng.verify_batch(agg, msgs, b"".join(pks), dst)
+    assert v == 1 and all(s == 0 for s in st)
+    msgs[n // 3] = bytes([msgs[n // 3][0] ^ 0x80]) + msgs[n // 3][1:]
+    v, _ = eng.verify_batch(agg, msgs, b"".join(pks), dst)
+    assert v == 0
+    # spot-check a few of the 262 144 signatures against the oracle's sign()
+    from oracle import noble_oracle as O
+    for i in (0, 1, 31, 32, 99999, n - 1):
+        m = hashlib.sha256(i.to_bytes(8, "big")).digest()
+        assert sigs[96 * i : 96 * i + 96] == O.sign(m, i + 1)
