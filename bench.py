@@ -114,17 +114,16 @@ def verify_section(eng, n, rank, world, dist, torch):
     from noble_bls12_381_b200 import synth
     dst = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
     P_ = synth.P
-    base = rank * n
-    # keys sk_i = base + i + 1 (public keys (sk_i * G1) come from the host-side synthetic generator)
-    g1_all, _ = synth.multiples_wire(base + n) if base else synth.multiples_wire(n)
-    g1 = g1_all[96 * base:]
+    # keys sk_i = i + 1 on every rank (public keys (i+1)*G1 from the host-side synthetic generator); the messages
+    # are distinct per (rank, i), so the world x n batch has world x n different (message, signature) pairs
+    g1, _ = synth.multiples_wire(n)
     pks = []
     for i in range(n):
         x = int.from_bytes(g1[96 * i: 96 * i + 48], "big")
         y = int.from_bytes(g1[96 * i + 48: 96 * i + 96], "big")
         pks.append((x + ((y * 2) // P_) * (1 << 381) + (1 << 383)).to_bytes(48, "big"))
-    msgs = [hashlib.sha256(b"msg" + (base + i).to_bytes(8, "big")).digest() for i in range(n)]
-    sks = b"".join((base + i + 1).to_bytes(32, "big") for i in range(n))
+    msgs = [hashlib.sha256(b"msg" + rank.to_bytes(2, "big") + i.to_bytes(8, "big")).digest() for i in range(n)]
+    sks = b"".join((i + 1).to_bytes(32, "big") for i in range(n))
     eng.sign_batch(sks[: 32 * 64], msgs[:64], dst)  # warm-up (program load)
     t0 = time.perf_counter()
     sigs = eng.sign_batch(sks, msgs, dst)

@@ -134,7 +134,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     for (int i = 0; i < nbuf; ++i)
         if ((p->staged_mask >> i & 1) && strides[i]) stage_est += 32u * strides[i];
     const size_t smem_est = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 16 + std::min<size_t>(stage_est, 20480) + 1024;
-    const int max_ctas = p->warps == 2 ? 8 : (p->warps == 4 ? 4 : 2);
+    const int max_ctas = p->warps == 2 ? 8 : (p->warps == 4 ? 4 : (p->warps == 6 ? 3 : 2));
     int ctas_per_sm = std::max(1, std::min(max_ctas, (int)(232448 / smem_est)));
     if (g.force_ctas > 0) ctas_per_sm = std::min(ctas_per_sm, g.force_ctas);
     const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)(g.sm_count * ctas_per_sm));
@@ -177,7 +177,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     g.launches.fetch_add(1);
     if (p->warps == 2) return launch_w<2, 8>(L, grid, smem, s);
     if (p->warps == 4) return launch_w<4, 4>(L, grid, smem, s);
-    if (p->warps == 6) return launch_w<6, 2>(L, grid, smem, s);
+    if (p->warps == 6) return ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
     if (p->warps == 8) return launch_w<8, 2>(L, grid, smem, s);
     if (p->warps == 10) return launch_w<10, 2>(L, grid, smem, s);
     return fail(BLS381_EPROGRAM, "unsupported warp count");

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
 template __global__ void vm_kernel<2, 8>(const Launch);
 template __global__ void vm_kernel<4, 4>(const Launch);
 template __global__ void vm_kernel<6, 2>(const Launch);
+template __global__ void vm_kernel<6, 3>(const Launch);
 template __global__ void vm_kernel<8, 2>(const Launch);
 template __global__ void vm_kernel<10, 2>(const Launch);
 
