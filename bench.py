@@ -27,30 +27,77 @@ IMAD_PER_PAIRING = FP_MUL_PER_PAIRING * IMAD_PER_FP_MUL  # ~4.44 M
 BYTES_PER_PAIRING = 288 + 576  # algorithmic HBM bytes
 
 
-def _clock_sampler(stop, samples):
-    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
+def issued_imad_per_item(program_path, wide_per_product=144):
+    """IMAD.WIDE the interpreter executes per item for a tower-VM program image: products x 144 (or 108 with the
+    Karatsuba core) + Montgomery reductions x 156, counted from the record headers (opcode 1 = MAC, T = bits 16..19)."""
+    import struct
+    raw = open(program_path, "rb").read()
+    _magic, _ver, warps, nrec, nconst, _ns, _nf, _st = struct.unpack_from("<8I", raw, 0)
+    base = 32 + nconst * 48
+    products = reductions = 0
+    for k in range(warps * nrec):
+        hdr = struct.unpack_from("<I", raw, base + k * 128)[0]
+        if hdr & 0xFF == 1:
+            t = (hdr >> 16) & 0xF
+            products += t
+            reductions += 1 if t else 0
+    return products * wide_per_product + reductions * 156, products, reductions
+
+
+class ClockSampler:
+    """One long-lived `nvidia-smi -lms 50` process (spawning a fresh nvidia-smi per sample takes longer than a step);
+    samples are time-stamped so that only those inside the timed region are summarised."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self):
+        self.samples = []
+        self.proc = None
         try:
-            out = subprocess.run(["nvidia-smi", "-i", os.environ.get("LOCAL_RANK", "0"), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                 capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
-            samples.append([x.strip() for x in out.split(",")])
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", os.environ.get("LOCAL_RANK", "0"), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
         except Exception:
-            pass
-        stop.wait(0.2)
+            self.proc = None
 
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 7:
+                self.samples.append((time.time(), f))
 
-def _clocks_summary(samples):
-    if not samples:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    sm = sorted(int(float(s[0])) for s in samples if s[0].replace(".", "").isdigit())
-    reasons = set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for s in samples:
-        for k, nm in enumerate(names):
-            if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
-                reasons.add(nm)
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(samples[0][1])) if samples[0][1] else None,
-            "reasons": sorted(reasons), "samples": len(samples)}
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1, kernel_mhz=None):
+        """median SM clock / reasons over the samples taken in [t0, t1] (the timed regions)"""
+        inside = [f for (t, f) in self.samples if t0 <= t <= t1]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(inside)}
+        if kernel_mhz:
+            out["sm_mhz_in_kernel"] = kernel_mhz
+            out["note"] = "sm_mhz_in_kernel = SM cycles / nanoseconds counted by CTA 0 of the last timed launch (clock64 vs globaltimer); the B200 settles well below its 1965 MHz boost under a sustained full-chip integer load (MEASURED_PEAKS.json: 1387 MHz under cuBLAS)"
+        if not self.samples:
+            out["reasons"] = ["nvidia-smi unavailable"]
+            return out
+        use = inside or [f for (_, f) in self.samples]
+        sm = sorted(int(float(f[0])) for f in use if f[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for f in use:
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        pw = [float(f[2]) for f in use if f[2].replace(".", "").isdigit()]
+        out.update({"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                    "sm_max_mhz": int(float(use[0][1])) if use[0][1] else None, "power_w_max": max(pw) if pw else None,
+                    "reasons": sorted(reasons)})
+        return out
 
 
 def cpu_baseline(total: int):
@@ -211,6 +258,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--program-dir", default=None, help="alternative tower-VM program directory (tuning)")
+    ap.add_argument("--wide-per-product", type=int, default=144, help="IMAD.WIDE per 384x384 product of the built Fp core (108 for -DBLS381_KARATSUBA)")
     ap.add_argument("--verify-n", type=int, default=65536, help="signatures per GPU for the verifyBatch / sign section (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -260,17 +308,18 @@ def main():
         k = min(n, 1000)
         parity = bytes(dout[: 576 * k].cpu().numpy().tobytes()) == open(gold_path, "rb").read()[: 576 * k]
 
-    stop, samples = threading.Event(), []
-    th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
-    th.start()
+    sampler = ClockSampler()
+    time.sleep(0.15)
     launches0 = eng.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    t_region0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
         step_resident()
         ev[i + 1].record(stream)
     barrier()
+    kernel_mhz = eng.last_kernel_sm_mhz()
     launches = eng.launch_count() - launches0
     ms_total = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -287,8 +336,8 @@ def main():
         assert rc == 0
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    stop.set()
-    th.join(timeout=2)
+    t_region1 = time.time()
+    sampler.stop()
     if parity:
         k = min(n, 1000)
         parity = bytes(hout[: 576 * k].numpy().tobytes()) == open(gold_path, "rb").read()[: 576 * k]
@@ -312,6 +361,9 @@ def main():
         except Exception:
             pass
         imad_peak = eng.imad_peak()
+        imad_sustained, imad_sustained_mhz = eng.imad_peak_sustained(1.0)
+        prog_dir = args.program_dir or os.path.join(ROOT, "noble_bls12_381_b200", "programs")
+        IMAD_ISSUED_PER_PAIRING, n_products, n_reductions = issued_imad_per_item(os.path.join(prog_dir, "pairing.b2vm"), args.wide_per_product)
         per_gpu = n / (ms_per_step * 1e-3)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
@@ -326,15 +378,19 @@ def main():
             "roofline": {
                 "bound": "imad", "achieved": per_gpu * IMAD_PER_PAIRING / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
                 "frac": per_gpu * IMAD_PER_PAIRING / imad_peak,
+                "peak_sustained": imad_sustained / 1e12, "peak_sustained_sm_mhz": imad_sustained_mhz,
+                "frac_sustained": per_gpu * IMAD_PER_PAIRING / imad_sustained,
+                "issued_per_pairing": {"imad_wide": IMAD_ISSUED_PER_PAIRING, "products": n_products, "reductions": n_reductions},
+                "issued": per_gpu * IMAD_ISSUED_PER_PAIRING / 1e12, "issued_frac_sustained": per_gpu * IMAD_ISSUED_PER_PAIRING / imad_sustained,
                 "traffic": None,
-                "note": "integer-multiply pipe bound (SURVEY 8d): achieved = pairings/s/GPU x 15.4k Fp-mul x 288 IMAD; peak = IMAD.WIDE.U32 issue rate measured live on this GPU (bls381_imad_peak)",
+                "note": "integer-multiply pipe bound (SURVEY 8d): achieved = pairings/s/GPU x 15.4k Fp-mul x 288 IMAD; peak = IMAD.WIDE.U32 issue rate measured live on this GPU in a 3 ms burst (bls381_imad_peak, boost clock); peak_sustained = the same microbenchmark back to back for 1 s (power-settled clock, the fair denominator for a step this long); issued = the multiply-adds the kernel actually executes (lazy-reduction program: more products, fewer reductions)",
                 "hbm": {"achieved": per_gpu * BYTES_PER_PAIRING / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * BYTES_PER_PAIRING / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             },
             "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": 288 * n, "d2h_bytes_per_step": 576 * n},
             "gpu_launches": int(launches),
-            "clocks": _clocks_summary(samples),
+            "clocks": sampler.summary(t_region0, t_region1, kernel_mhz),
             "input_generation_s": t_gen,
         }
         if vb is not None:

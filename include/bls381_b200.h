@@ -145,6 +145,11 @@ uint64_t bls381_launch_count(void);
 int bls381_imad_peak(double* imad_per_second);
 /* device time in milliseconds of the last tower-VM kernel launched through a host entry point */
 double bls381_last_kernel_ms(void);
+/* effective SM clock (MHz) during the last tower-VM launch: cycles / nanoseconds seen by CTA 0 (clock64 vs globaltimer) */
+double bls381_last_kernel_sm_mhz(void);
+/* the same microbenchmark launched back to back for `seconds`; reports the rate of the second half (the sustained
+ * figure, with power and clocks settled) and the effective SM clock of its last launch */
+int bls381_imad_peak_sustained(double seconds, double* imad_per_second, double* sm_mhz);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbls381_b200.so")
+LIB_PATH = os.environ.get("BLS381_B200_LIB") or os.path.join(_HERE, "libbls381_b200.so")  # env override: tuning builds
 
 
 class EngineError(RuntimeError):
@@ -24,6 +24,8 @@ def _load():
     lib.bls381_last_error.restype = ctypes.c_char_p
     lib.bls381_launch_count.restype = ctypes.c_uint64
     lib.bls381_last_kernel_ms.restype = ctypes.c_double
+    lib.bls381_last_kernel_sm_mhz.restype = ctypes.c_double
+    lib.bls381_imad_peak_sustained.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     for name in ("bls381_pairing_batch",):
         getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_pairing_batch_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -54,7 +56,8 @@ EXPORTS = [
     "bls381_init", "bls381_shutdown", "bls381_last_error", "bls381_sm_count",
     "bls381_pairing_batch", "bls381_pairing_batch_dev", "bls381_final_exp_batch", "bls381_final_exp_batch_dev",
     "bls381_miller_product", "bls381_miller_product_dev", "bls381_vm_run_dev", "bls381_vm_load",
-    "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms",
+    "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms", "bls381_last_kernel_sm_mhz",
+    "bls381_imad_peak_sustained",
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
     "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
     "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_g1_scalar_mul_batch", "bls381_verify_batch_partial",
@@ -209,6 +212,16 @@ class Engine:
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.bls381_last_kernel_ms())
+
+    def last_kernel_sm_mhz(self) -> float:
+        """effective SM clock during the last tower-VM launch (clock64 / globaltimer of CTA 0)"""
+        return float(self.lib.bls381_last_kernel_sm_mhz())
+
+    def imad_peak_sustained(self, seconds: float = 1.0):
+        """(multiply-adds/s, SM MHz) of the IMAD.WIDE microbenchmark run back to back for `seconds`"""
+        v, m = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self.lib.bls381_imad_peak_sustained(seconds, ctypes.byref(v), ctypes.byref(m)))
+        return v.value, m.value
 
     def sm_count(self) -> int:
         return int(self.lib.bls381_sm_count())

@@ -31,6 +31,7 @@ struct State {
     int sm_count = 0;
     std::map<std::string, Program> programs;
     uint32_t* d_far = nullptr;
+    unsigned long long* d_clk = nullptr;  // clock probe of the last tower-VM launch {cycles, ns}
     size_t far_bytes = 0;
     // grow-only device staging for the host entry points
     static constexpr int kStages = 10;
@@ -174,12 +175,51 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     }
     L.stage_bytes = stage_bytes;
     const size_t smem = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 16 + stage_bytes;  // slots + constants + progress + mbarrier + staging
+    // debug tracing (env BLS381_B200_TRACE=<file prefix>): clocks of every record of the first two CTAs
+    uint32_t* d_trace = nullptr;
+    uint32_t* d_log = nullptr;
+    const char* trace_prefix = getenv("BLS381_B200_TRACE");
+    const uint32_t trace_ctas = 2;
+    if (trace_prefix && *trace_prefix) {
+        CUDA_TRY(cudaMalloc(&d_trace, (size_t)trace_ctas * p->warps * p->nrec * 12));
+        CUDA_TRY(cudaMemset(d_trace, 0, (size_t)trace_ctas * p->warps * p->nrec * 12));
+        L.trace = d_trace;
+        L.trace_ctas = trace_ctas;
+        CUDA_TRY(cudaMalloc(&d_log, (size_t)grid * 16 * 16));
+        CUDA_TRY(cudaMemset(d_log, 0, (size_t)grid * 16 * 16));
+        L.cta_log = d_log;
+    }
+    L.clk = g.d_clk;
     g.launches.fetch_add(1);
-    if (p->warps == 2) return launch_w<2, 8>(L, grid, smem, s);
-    if (p->warps == 4) return launch_w<4, 4>(L, grid, smem, s);
-    if (p->warps == 6) return ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
-    if (p->warps == 8) return launch_w<8, 2>(L, grid, smem, s);
-    if (p->warps == 10) return launch_w<10, 2>(L, grid, smem, s);
+    rc = BLS381_EPROGRAM;
+    if (p->warps == 2) rc = launch_w<2, 8>(L, grid, smem, s);
+    if (p->warps == 4) rc = launch_w<4, 4>(L, grid, smem, s);
+    if (p->warps == 6) rc = ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
+    if (p->warps == 8) rc = launch_w<8, 2>(L, grid, smem, s);
+    if (p->warps == 10) rc = launch_w<10, 2>(L, grid, smem, s);
+    if (d_trace) {
+        cudaStreamSynchronize(s);
+        std::vector<uint32_t> h((size_t)trace_ctas * p->warps * p->nrec * 3);
+        cudaMemcpy(h.data(), d_trace, h.size() * 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        const std::string path = std::string(trace_prefix) + "_" + name + ".bin";
+        if (FILE* f = fopen(path.c_str(), "wb")) {
+            uint32_t hdr4[4] = {trace_ctas, p->warps, p->nrec, 3};
+            fwrite(hdr4, 4, 4, f);
+            fwrite(h.data(), 4, h.size(), f);
+            fclose(f);
+        }
+        std::vector<uint32_t> hl((size_t)grid * 16 * 4);
+        cudaMemcpy(hl.data(), d_log, hl.size() * 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_log);
+        if (FILE* f = fopen((std::string(trace_prefix) + "_" + name + "_ctas.bin").c_str(), "wb")) {
+            uint32_t hdr4[4] = {(uint32_t)grid, 16, 4, (uint32_t)n};
+            fwrite(hdr4, 4, 4, f);
+            fwrite(hl.data(), 4, hl.size(), f);
+            fclose(f);
+        }
+    }
+    if (rc != BLS381_EPROGRAM) return rc;
     return fail(BLS381_EPROGRAM, "unsupported warp count");
 }
 
@@ -325,7 +365,13 @@ int aggregate_dev(bool g2, uint8_t* d_affine, int32_t* d_status, size_t n, uint8
 }
 
 // ---- IMAD.WIDE issue-rate microbenchmark -------------------------------------------------------
-__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters) {
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters, unsigned long long* clk) {
+    unsigned long long probe_c = 0, probe_t = 0;
+    const bool probing = clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (probing) {
+        probe_c = (unsigned long long)clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(probe_t));
+    }
     uint64_t acc[4][6];
     uint32_t ct[4] = {0, 0, 0, 0};
     const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
@@ -345,6 +391,12 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, int iters
 #pragma unroll
         for (int i = 0; i < 6; ++i) x ^= (uint32_t)acc[k][i] ^ (uint32_t)(acc[k][i] >> 32);
     out[t] = x ^ ct[1] ^ ct[2] ^ ct[3];
+    if (probing) {
+        unsigned long long tt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        clk[0] = (unsigned long long)clock64() - probe_c;
+        clk[1] = tt - probe_t;
+    }
 }
 
 }  // namespace
@@ -378,6 +430,8 @@ int bls381_init(int device, const char* program_dir) {
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
+    CUDA_TRY(cudaMalloc(&g.d_clk, 16));
+    CUDA_TRY(cudaMemset(g.d_clk, 0, 16));
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g.ev0));
@@ -400,6 +454,8 @@ int bls381_shutdown(void) {
     if (g.d_far) cudaFree(g.d_far);
     g.d_far = nullptr;
     g.far_bytes = 0;
+    if (g.d_clk) cudaFree(g.d_clk);
+    g.d_clk = nullptr;
     for (int k = 0; k < State::kStages; ++k) {
         if (g.d_stage[k]) cudaFree(g.d_stage[k]);
         g.d_stage[k] = nullptr;
@@ -419,6 +475,14 @@ const char* bls381_last_error(void) { return g_err.c_str(); }
 int bls381_sm_count(void) { return g.inited ? g.sm_count : 0; }
 uint64_t bls381_launch_count(void) { return g.launches.load(); }
 double bls381_last_kernel_ms(void) { return g.last_ms; }
+
+double bls381_last_kernel_sm_mhz(void) {
+    if (!g.inited || !g.d_clk) return 0.0;
+    unsigned long long h[2] = {0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return 0.0;
+    if (cudaMemcpy(h, g.d_clk, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess || h[1] == 0) return 0.0;
+    return (double)h[0] / (double)h[1] * 1000.0;
+}
 
 int bls381_vm_load(const char* name, const uint8_t* image, size_t len) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -804,11 +868,11 @@ int bls381_imad_peak(double* imad_per_second) {
     const int blocks = g.sm_count * 8, threads = 256, iters = 4096;
     uint32_t* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, (size_t)blocks * threads * 4));
-    imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, 64);  // warm-up
+    imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, 64, nullptr);  // warm-up
     double best = 0;
     for (int rep = 0; rep < 5; ++rep) {
         CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-        imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, iters);
+        imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, iters, nullptr);
         CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
         CUDA_TRY(cudaStreamSynchronize(g.stream));
         float ms = 0;
@@ -818,6 +882,37 @@ int bls381_imad_peak(double* imad_per_second) {
     }
     cudaFree(d);
     *imad_per_second = best;
+    return BLS381_OK;
+}
+
+int bls381_imad_peak_sustained(double seconds, double* imad_per_second, double* sm_mhz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!imad_per_second || !(seconds > 0) || seconds > 10) return fail(BLS381_EINVAL, "bad argument");
+    const int blocks = g.sm_count * 8, threads = 256, iters = 4096;
+    const double ops = (double)blocks * threads * iters * 24.0;
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    // back-to-back launches for `seconds`; the rate is taken over the second half, when clocks and power have settled
+    const int chunk = 16;
+    double elapsed = 0, rate = 0;
+    while (elapsed < seconds) {
+        CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+        for (int k = 0; k < chunk; ++k) imad_peak_kernel<<<blocks, threads, 0, g.stream>>>(d, iters, g.d_clk);
+        CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+        elapsed += ms * 1e-3;
+        if (elapsed >= seconds * 0.5) rate = rate == 0 ? ops * chunk / (ms * 1e-3) : std::min(rate, ops * chunk / (ms * 1e-3));
+    }
+    cudaFree(d);
+    *imad_per_second = rate;
+    if (sm_mhz) {
+        unsigned long long h[2] = {0, 0};
+        CUDA_TRY(cudaMemcpy(h, g.d_clk, sizeof(h), cudaMemcpyDeviceToHost));
+        *sm_mhz = h[1] ? (double)h[0] / (double)h[1] * 1000.0 : 0.0;
+    }
     return BLS381_OK;
 }
 

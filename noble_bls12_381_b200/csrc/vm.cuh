@@ -88,7 +88,10 @@ struct Launch {
     // bulk-copied into shared memory at the start of every batch; kNoStage = read directly from global memory
     uint32_t stage_off[kMaxBuffers];   // byte offset inside the staging area
     uint32_t stage_bytes;              // total staging bytes (multiple of 16)
-    uint32_t pad2;
+    uint32_t trace_ctas;               // tracing (debug): CTAs 0..trace_ctas-1 record 3 clocks per record
+    uint32_t* trace;                   // [trace_ctas][warps][nrec][3] (start, after waits, end), first batch only
+    uint32_t* cta_log;                 // tracing (debug): [grid][16][4] = {smid, batch, start ns, end ns} per CTA and batch round
+    unsigned long long* clk;           // clock probe: CTA 0 stores {SM cycles, nanoseconds} it spent in this launch (or null)
 };
 static constexpr uint32_t kNoStage = 0xFFFFFFFFu;
 

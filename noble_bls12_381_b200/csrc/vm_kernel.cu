@@ -29,6 +29,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     }
     uint32_t phase = 0;
     for (uint32_t i = threadIdx.x; i < L.nconst * 12; i += blockDim.x) sconst[i] = L.consts[i];
+    // clock probe: effective SM clock of this launch = cycles / nanoseconds seen by CTA 0 (bench.py reports it:
+    // nvidia-smi sampling is too coarse for a 50 ms step)
+    unsigned long long probe_c = 0, probe_t = 0;
+    const bool probing = L.clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (probing) {
+        probe_c = (unsigned long long)clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(probe_t));
+    }
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nbatch = (L.n_items + 31) / 32;
@@ -44,13 +52,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     c.stage = L.stage_bytes ? stage : nullptr;
     c.stage_off = L.stage_off;
 
-    for (uint32_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    // Static round-robin split of the batches.  The two CTAs sharing an SM do NOT run at the same speed (measured
+    // 6.2 ms vs 10.0 ms per batch: the warp scheduler favours the older CTA; one CTA alone needs 5.0 ms), but claiming
+    // batches dynamically from a global counter was measured 1.7 % slower at 65536 items: the batch is too coarse a
+    // quantum for the tail to balance (profiles/r1_notes.md)
+    uint32_t round = 0;
+    for (uint32_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x, ++round) {
         const uint32_t item = batch * 32 + lane;
         c.store_ok = item < L.n_items;
         c.item = c.store_ok ? item : L.n_items - 1;
         c.batch = batch;
         __syncthreads();  // previous batch fully retired (and constants visible)
         if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+        if (L.cta_log != nullptr && threadIdx.x == 0) {
+            if (round < 16) {
+                uint32_t smid;
+                unsigned long long t;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                uint32_t* lp = L.cta_log + ((size_t)blockIdx.x * 16 + round) * 4;
+                lp[0] = smid; lp[1] = batch; lp[2] = (uint32_t)t;
+                if (round > 0) lp[-1] = (uint32_t)t;  // end of the previous round
+            }
+        }
         if (L.stage_bytes) {
             // stage this batch's wire-format inputs: one elected thread issues 1-D bulk copies (TMA) of the batch's
             // contiguous record block of every staged buffer; everybody then waits on the mbarrier phase
@@ -86,6 +110,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
         for (uint32_t r = 0; r < L.nrec; ++r) {
             const uint32_t cur = next;
             if (r + 1 < L.nrec) next = stream[(size_t)(r + 1) * kRecWords + lane];  // prefetch
+            const bool tracing = L.trace != nullptr && blockIdx.x < L.trace_ctas && round == 0;
+            uint32_t t0 = 0, t1 = 0;
+            if (tracing) t0 = (uint32_t)clock64();
             const uint32_t hdr = __shfl_sync(0xffffffffu, cur, 0);
             const uint32_t aux = __shfl_sync(0xffffffffu, cur, 1);
             if (hdr & H_BAR) {  // this record carries progress requirements
@@ -111,13 +138,33 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
                 __threadfence_block();
                 __syncwarp();
             }
+            if (tracing) t1 = (uint32_t)clock64();
             exec_record(c, hdr, aux, [&](uint32_t i) { return __shfl_sync(0xffffffffu, cur, i); });
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
                 progress[warp] = r + 1;
+                if (tracing) {
+                    uint32_t* tp = L.trace + (((size_t)blockIdx.x * WARPS + warp) * L.nrec + r) * 3;
+                    tp[0] = t0; tp[1] = t1; tp[2] = (uint32_t)clock64();
+                }
             }
         }
+    }
+    if (L.cta_log != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0 && blockIdx.x < nbatch) {
+            const uint32_t rounds = round;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (rounds >= 1 && rounds <= 16) L.cta_log[((size_t)blockIdx.x * 16 + rounds - 1) * 4 + 3] = (uint32_t)t;
+        }
+    }
+    if (probing) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        L.clk[0] = (unsigned long long)clock64() - probe_c;
+        L.clk[1] = t - probe_t;
     }
 }
 

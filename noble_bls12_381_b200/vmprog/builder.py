@@ -33,6 +33,7 @@ H_BAR, H_DSTG, H_DSTWORD, H_DSTBATCH, H_PADCONST, H_POST_ISZERO, H_POST_GTHALF =
 REC_WORDS = 32
 MAX_TERMS = 12
 MAX_SUM_BOUND = 80.0  # sum of |x|*|y| bounds in units of p^2 that fits the 768-bit accumulator
+COST_MODEL = "v2"  # "v1" = the instruction-count estimate used before the trace calibration
 MAX_K = 9.5  # result bound (units of p): must stay below 2^384 / p = 9.84; `correct` handles up to 4 rounds
 
 
@@ -187,14 +188,24 @@ class Op:
     tag: str = ""
 
     def cost(self):
-        """Estimated duration in units of one 12x12 product (calibrated on the ncu instruction counts: a
-        product ~300 issued instructions, per-op reduction/correction/decode overhead ~500)."""
+        """Estimated duration in units of one 12x12 product.  Calibrated on the per-record clock trace of the
+        pairing program on a B200 (profiles/r1_notes.md): cycles ~ 2500 + 1700*T + 1100*E + 125*ncorr for a
+        multiply-accumulate record, ~1600 for an epilogue-only record, ~193 k for the inversion."""
+        if COST_MODEL == "v1":
+            if self.kind == "inv":
+                return 235.0
+            if self.kind != "mac":
+                return 0.5
+            t = len(self.terms)
+            return (t + 1.7 if t else 0.6) + 0.1 * len(self.epi)
         if self.kind == "inv":
-            return 235.0  # 25 outer iterations of the binary GCD, ~55 k instructions
+            return 114.0
         if self.kind != "mac":
-            return 0.5
+            return 0.4
         t = len(self.terms)
-        return (t + 1.7 if t else 0.6) + 0.1 * len(self.epi)
+        if not t:
+            return 0.6 + 0.35 * len(self.epi) + 0.07 * self.ncorr
+        return t + 1.5 + 0.65 * len(self.epi) + 0.07 * self.ncorr
 
     def src_vals(self):
         vs = []

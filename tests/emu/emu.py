@@ -11,7 +11,7 @@ _LIB = None
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(HERE, "_build", "libvm_emu.so")
+        so = os.environ.get("BLS381_EMU_LIB") or os.path.join(HERE, "_build", "libvm_emu.so")
         src = os.path.join(HERE, "vm_emu.cpp")
         deps = [src] + [os.path.join(ROOT, "noble_bls12_381_b200", "csrc", f) for f in ("vm.cuh", "fp_core.cuh", "fp_core_gen.cuh", "fp_inv.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
