@@ -31,6 +31,8 @@ struct State {
     int sm_count = 0;
     std::map<std::string, Program> programs;
     uint32_t* d_far = nullptr;
+    static constexpr int kTickets = 4096;
+    int dynamic_batches = 1;  // batches claimed from a global counter (+4.9 % at 65536 pairings, profiles/r1_notes.md)
     unsigned long long* d_clk = nullptr;  // clock probe of the last tower-VM launch {cycles, ns}
     size_t far_bytes = 0;
     // grow-only device staging for the host entry points
@@ -75,6 +77,7 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
     if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    if (p.nrec == 0 || p.nrec > 65535) return fail(BLS381_EPROGRAM, "record count out of range (16-bit progress counters): " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
@@ -181,8 +184,8 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     const char* trace_prefix = getenv("BLS381_B200_TRACE");
     const uint32_t trace_ctas = 2;
     if (trace_prefix && *trace_prefix) {
-        CUDA_TRY(cudaMalloc(&d_trace, (size_t)trace_ctas * p->warps * p->nrec * 12));
-        CUDA_TRY(cudaMemset(d_trace, 0, (size_t)trace_ctas * p->warps * p->nrec * 12));
+        CUDA_TRY(cudaMalloc(&d_trace, (size_t)trace_ctas * p->warps * p->nrec * 32));
+        CUDA_TRY(cudaMemset(d_trace, 0, (size_t)trace_ctas * p->warps * p->nrec * 32));
         L.trace = d_trace;
         L.trace_ctas = trace_ctas;
         CUDA_TRY(cudaMalloc(&d_log, (size_t)grid * 16 * 16));
@@ -190,6 +193,10 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
         L.cta_log = d_log;
     }
     L.clk = g.d_clk;
+    if (g.dynamic_batches) {  // one counter per launch (a ring: launches on the two internal streams may overlap)
+        L.ticket = reinterpret_cast<uint32_t*>(g.d_clk + 2) + (g.launches.load() % State::kTickets);
+        CUDA_TRY(cudaMemsetAsync(L.ticket, 0, 4, s));
+    }
     g.launches.fetch_add(1);
     rc = BLS381_EPROGRAM;
     if (p->warps == 2) rc = launch_w<2, 8>(L, grid, smem, s);
@@ -199,12 +206,12 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     if (p->warps == 10) rc = launch_w<10, 2>(L, grid, smem, s);
     if (d_trace) {
         cudaStreamSynchronize(s);
-        std::vector<uint32_t> h((size_t)trace_ctas * p->warps * p->nrec * 3);
+        std::vector<uint32_t> h((size_t)trace_ctas * p->warps * p->nrec * 8);
         cudaMemcpy(h.data(), d_trace, h.size() * 4, cudaMemcpyDeviceToHost);
         cudaFree(d_trace);
         const std::string path = std::string(trace_prefix) + "_" + name + ".bin";
         if (FILE* f = fopen(path.c_str(), "wb")) {
-            uint32_t hdr4[4] = {trace_ctas, p->warps, p->nrec, 3};
+            uint32_t hdr4[4] = {trace_ctas, p->warps, p->nrec, 8};
             fwrite(hdr4, 4, 4, f);
             fwrite(h.data(), 4, h.size(), f);
             fclose(f);
@@ -430,8 +437,9 @@ int bls381_init(int device, const char* program_dir) {
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
-    CUDA_TRY(cudaMalloc(&g.d_clk, 16));
-    CUDA_TRY(cudaMemset(g.d_clk, 0, 16));
+    if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
+    CUDA_TRY(cudaMalloc(&g.d_clk, 16 + 4 * State::kTickets));  // {cycles, ns} clock probe + batch ticket counters
+    CUDA_TRY(cudaMemset(g.d_clk, 0, 16 + 4 * State::kTickets));
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g.ev0));

@@ -56,7 +56,7 @@ static constexpr int kConstSlots = 64;
 //                       bits to clear (compression flags), cB = 0: 48-byte field, 1: 32-byte field)
 //                  bit2 XLANE  (read the slot column of lane ^ mask)
 //                  bit3 SIMPLE (operand is exactly one shared-memory slot, coefficient +1: fast path)
-//                  bits 4..6: pre-decoded fast mode for shared-memory slots: 1 = -A, 2 = A+B, 3 = A-B, 4 = -A-B
+//                  bits 4..6: pre-decoded fast mode for shared-memory slots: 1 = -A, 2 = A+B, 3 = A-B, 4 = -A-B, 5 = 2A
 enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3, OP_INV = 4 };
 enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8 };
 static constexpr uint32_t H_BAR = 1u << 25;
@@ -89,8 +89,9 @@ struct Launch {
     uint32_t stage_off[kMaxBuffers];   // byte offset inside the staging area
     uint32_t stage_bytes;              // total staging bytes (multiple of 16)
     uint32_t trace_ctas;               // tracing (debug): CTAs 0..trace_ctas-1 record 3 clocks per record
-    uint32_t* trace;                   // [trace_ctas][warps][nrec][3] (start, after waits, end), first batch only
+    uint32_t* trace;                   // [trace_ctas][warps][nrec][8] (start, after waits, end, 5 phase durations), first batch only
     uint32_t* cta_log;                 // tracing (debug): [grid][16][4] = {smid, batch, start ns, end ns} per CTA and batch round
+    uint32_t* ticket;                  // dynamic batch assignment (or null): next unclaimed batch - gridDim.x, zeroed before the launch
     unsigned long long* clk;           // clock probe: CTA 0 stores {SM cycles, nanoseconds} it spent in this launch (or null)
 };
 static constexpr uint32_t kNoStage = 0xFFFFFFFFu;
@@ -228,22 +229,36 @@ FPC_DEV void load_near(uint32_t* r, const Ctx& c, uint32_t slot) {
 #endif
 }
 
+// r = 2*r (no reduction; r < 2^383): funnel shifts, no carry chain
+FPC_DEV void shl1_raw(uint32_t* r) {
+#pragma unroll
+    for (int k = 11; k > 0; --k) r[k] = (r[k] << 1) | (r[k - 1] >> 31);
+    r[0] <<= 1;
+}
+
+// Pre-decoded operand modes on shared-memory slots (bits 27..30 of the operand word): SIMPLE = +A; fast modes
+// 1 = -A, 2 = A+B, 3 = A-B, 4 = -A-B, 5 = 2A.  Everything else takes the general path.
+FPC_DEV bool operand_is_near(uint32_t w) { return (w & ((F_SIMPLE << 24) | (0x7u << 28))) != 0; }
+
+// second half of a near operand whose A slot is already in r (load_near issued earlier, see exec_record)
+FPC_DEV void finish_near_operand(uint32_t* r, const Ctx& c, uint32_t w) {
+    if (w & (F_SIMPLE << 24)) return;
+    const uint32_t fast = (w >> 28) & 0x7;
+    if (fast == 1) { fpc::neg_raw(r, r); return; }
+    if (fast == 5) { shl1_raw(r); return; }
+    uint32_t u[12];
+    load_near(u, c, (w >> 8) & 0xFF);
+    if (fast == 2) { (void)fpc::add12(r, r, u); return; }
+    if (fast == 3) { fpc::neg_raw(u, u); (void)fpc::add12(r, r, u); return; }
+    (void)fpc::add12(r, r, u);   // fast == 4: -A - B = 2p - (A + B)
+    fpc::neg_raw2(r, r);
+}
+
 // operand = cA*A + cB*B  (negative coefficients via p - X), unreduced
 FPC_DEV void load_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask) {
-    if (w & (F_SIMPLE << 24)) {
+    if (operand_is_near(w)) {
         load_near(r, c, w & 0xFF);
-        return;
-    }
-    const uint32_t fast = (w >> 28) & 0x7;
-    if (fast) {  // pre-decoded modes on shared-memory slots
-        load_near(r, c, w & 0xFF);
-        if (fast == 1) { fpc::neg_raw(r, r); return; }
-        uint32_t u[12];
-        load_near(u, c, (w >> 8) & 0xFF);
-        if (fast == 2) { (void)fpc::add12(r, r, u); return; }
-        if (fast == 3) { fpc::neg_raw(u, u); (void)fpc::add12(r, r, u); return; }
-        (void)fpc::add12(r, r, u);   // fast == 4: -A - B = 2p - (A + B)
-        fpc::neg_raw2(r, r);
+        finish_near_operand(r, c, w);
         return;
     }
     const uint32_t a = w & 0xFF, b = (w >> 8) & 0xFF, flags = w >> 24;
@@ -264,9 +279,28 @@ FPC_DEV void load_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask)
     }
 }
 
-// Executes one record for one lane.  `W(i)` returns record word i (warp shuffle on device).
-template <class WordFn>
-FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
+// both operands of a product: the raw A-slot loads of x AND y are issued before either operand is completed, so
+// that y's shuffle + shared-memory latency overlaps x's negation / addition chains
+FPC_DEV void load_operand_pair(uint32_t* x, uint32_t* y, const Ctx& c, uint32_t wx, uint32_t wy, uint32_t xmask) {
+    const bool nx = operand_is_near(wx), ny = operand_is_near(wy);
+    if (nx) load_near(x, c, wx & 0xFF);
+    if (ny) load_near(y, c, wy & 0xFF);
+    if (nx) finish_near_operand(x, c, wx); else load_operand(x, c, wx, xmask);
+    if (ny) finish_near_operand(y, c, wy); else load_operand(y, c, wy, xmask);
+}
+
+FPC_DEV uint32_t phase_clock() {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)clock64();
+#else
+    return 0;
+#endif
+}
+
+// TRACE: ph[0..4] receive the cycles spent in operand loads, multiply-accumulates, the Montgomery reduction,
+// epilogue + correction, and the store (debug tracing only; the normal instantiation has no clock reads)
+template <bool TRACE = false, class WordFn>
+FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W, uint32_t* ph = nullptr) {
     const uint32_t op = hdr & 0xFF;
     if (op == OP_NOP) return;
     const uint32_t dst = (hdr >> 8) & 0xFF;
@@ -299,13 +333,25 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
     } else if (T > 0) {
         fpc::Acc A;
         fpc::acc_zero(A);
+        uint32_t nwx = W(2), nwy = W(3);
         for (uint32_t t = 0; t < T; ++t) {
             uint32_t x[12], y[12];
-            load_operand(x, c, W(2 + 2 * t), xmask);
-            load_operand(y, c, W(3 + 2 * t), xmask);
+            uint32_t k0 = 0, k1 = 0;
+            if (TRACE) k0 = phase_clock();
+            const uint32_t wx = nwx, wy = nwy;
+            // the operand words of the NEXT product are fetched (warp shuffles) before this product's loads, so their
+            // latency is hidden behind the multiply-accumulate (words 26.. of the last iteration are never used as terms)
+            nwx = W(4 + 2 * t);
+            nwy = W(5 + 2 * t);
+            load_operand_pair(x, y, c, wx, wy, xmask);
+            if (TRACE) { k1 = phase_clock() + (x[0] & y[0] & 0u); ph[0] += k1 - k0; }
             fpc::acc_mac(A, x, y);
+            if (TRACE) ph[1] += phase_clock() + (uint32_t)(A.e[11] & 0u) - k1;
         }
+        uint32_t k2 = 0;
+        if (TRACE) k2 = phase_clock();
         fpc::acc_redc(A, r);
+        if (TRACE) ph[2] += phase_clock() + (r[11] & 0u) - k2;
         if (!(hdr & H_PADCONST)) {  // common integer factor of all products, applied once to the reduced sum
             const uint32_t ps = aux >> 24;
             if (ps > 1) scale_raw(r, (int)ps);
@@ -313,12 +359,16 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
     } else {
         fpc::zero12(r);
     }
+    uint32_t k3 = 0;
+    if (TRACE) k3 = phase_clock();
     for (uint32_t e = 0; e < E; ++e) {
         uint32_t z[12];
         load_operand(z, c, W(26 + 2 * e), xmask);
         (void)fpc::add12(r, r, z);
     }
     fpc::correct(r, ncorr);
+    uint32_t k4 = 0;
+    if (TRACE) { k4 = phase_clock() + (r[11] & 0u); ph[3] += k4 - k3; }
     if (hdr & (H_POST_ISZERO | H_POST_GTHALF)) {
         uint32_t flag;
         if ((hdr & H_POST_ISZERO) && (hdr & H_POST_GTHALF)) {
@@ -345,6 +395,7 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
     } else {
         store_slot(r, c, dst);
     }
+    if (TRACE) ph[4] += phase_clock() - k4;
 }
 
 }  // namespace vm

@@ -52,12 +52,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     c.stage = L.stage_bytes ? stage : nullptr;
     c.stage_off = L.stage_off;
 
-    // Static round-robin split of the batches.  The two CTAs sharing an SM do NOT run at the same speed (measured
-    // 6.2 ms vs 10.0 ms per batch: the warp scheduler favours the older CTA; one CTA alone needs 5.0 ms), but claiming
-    // batches dynamically from a global counter was measured 1.7 % slower at 65536 items: the batch is too coarse a
-    // quantum for the tail to balance (profiles/r1_notes.md)
+    // Batch assignment: static round-robin, or (L.ticket != nullptr) claimed dynamically from a global counter.  The two
+    // CTAs sharing an SM do NOT run at the same speed (measured 6.2 ms vs 10.0 ms per batch: the warp scheduler favours
+    // one CTA; a CTA alone needs 5.0 ms), so with the static split the favoured CTAs finish early (profiles/r1_notes.md)
+    __shared__ uint32_t next_batch;
     uint32_t round = 0;
-    for (uint32_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x, ++round) {
+    for (uint32_t batch = blockIdx.x; batch < nbatch; ++round) {
         const uint32_t item = batch * 32 + lane;
         c.store_ok = item < L.n_items;
         c.item = c.store_ok ? item : L.n_items - 1;
@@ -110,7 +110,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
         for (uint32_t r = 0; r < L.nrec; ++r) {
             const uint32_t cur = next;
             if (r + 1 < L.nrec) next = stream[(size_t)(r + 1) * kRecWords + lane];  // prefetch
+#if defined(BLS381_VM_TRACE)   // tracing build only (tools/build_trace_lib.sh): per-record clocks of the first CTAs
             const bool tracing = L.trace != nullptr && blockIdx.x < L.trace_ctas && round == 0;
+#else
+            constexpr bool tracing = false;
+#endif
             uint32_t t0 = 0, t1 = 0;
             if (tracing) t0 = (uint32_t)clock64();
             const uint32_t hdr = __shfl_sync(0xffffffffu, cur, 0);
@@ -139,16 +143,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
                 __syncwarp();
             }
             if (tracing) t1 = (uint32_t)clock64();
-            exec_record(c, hdr, aux, [&](uint32_t i) { return __shfl_sync(0xffffffffu, cur, i); });
+            uint32_t ph[5] = {0, 0, 0, 0, 0};
+#if defined(BLS381_VM_TRACE)
+            if (tracing) exec_record<true>(c, hdr, aux, [&](uint32_t i) { return __shfl_sync(0xffffffffu, cur, i); }, ph);
+            else
+#endif
+            exec_record<false>(c, hdr, aux, [&](uint32_t i) { return __shfl_sync(0xffffffffu, cur, i); });
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
                 progress[warp] = r + 1;
                 if (tracing) {
-                    uint32_t* tp = L.trace + (((size_t)blockIdx.x * WARPS + warp) * L.nrec + r) * 3;
+                    uint32_t* tp = L.trace + (((size_t)blockIdx.x * WARPS + warp) * L.nrec + r) * 8;
                     tp[0] = t0; tp[1] = t1; tp[2] = (uint32_t)clock64();
+                    tp[3] = ph[0]; tp[4] = ph[1]; tp[5] = ph[2]; tp[6] = ph[3]; tp[7] = ph[4];
                 }
             }
+        }
+        if (L.ticket != nullptr) {
+            if (threadIdx.x == 0) next_batch = gridDim.x + atomicAdd(L.ticket, 1u);
+            __syncthreads();
+            batch = next_batch;
+        } else {
+            batch += gridDim.x;
         }
     }
     if (L.cta_log != nullptr) {

@@ -829,6 +829,8 @@ class Builder:
                 flags |= 3 << 4
             elif (o.ca, cb) == (-1, -1):
                 flags |= 4 << 4
+            elif (o.ca, cb) == (2, 0):
+                flags |= 5 << 4
         return a | (b << 8) | ((o.ca & 0xF) << 16) | ((o.cb & 0xF) << 20) | (flags << 24)
 
     def encode(self):
