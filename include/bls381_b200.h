@@ -139,6 +139,11 @@ int bls381_vm_run_dev(const char* program, uint8_t* const* d_bufs, const uint32_
 /* Loads a program from memory (file image) under `name`, replacing any previous one. */
 int bls381_vm_load(const char* name, const uint8_t* image, size_t len);
 
+/* Engine tuning knobs (same as the BLS381_B200_* environment variables read by bls381_init): "dynamic_batches" (1 = CTAs
+ * claim 32-item batches from a global counter, 0 = round-robin), "ctas_per_sm" (0 = automatic), "poll_sleep_ns",
+ * "no_tma" (1 = read wire-format inputs directly from global memory).  Results never depend on them.            */
+int bls381_set_option(const char* name, int value);
+
 /* Measurement aids (bench.py): number of tower-VM kernel launches since init, and a dependent-free
  * IMAD.WIDE.U32 issue-rate microbenchmark (returns multiply-adds per second on the whole device). */
 uint64_t bls381_launch_count(void);

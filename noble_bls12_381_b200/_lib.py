@@ -25,6 +25,7 @@ def _load():
     lib.bls381_launch_count.restype = ctypes.c_uint64
     lib.bls381_last_kernel_ms.restype = ctypes.c_double
     lib.bls381_last_kernel_sm_mhz.restype = ctypes.c_double
+    lib.bls381_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
     lib.bls381_imad_peak_sustained.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     for name in ("bls381_pairing_batch",):
         getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -57,7 +58,7 @@ EXPORTS = [
     "bls381_pairing_batch", "bls381_pairing_batch_dev", "bls381_final_exp_batch", "bls381_final_exp_batch_dev",
     "bls381_miller_product", "bls381_miller_product_dev", "bls381_vm_run_dev", "bls381_vm_load",
     "bls381_launch_count", "bls381_imad_peak", "bls381_last_kernel_ms", "bls381_last_kernel_sm_mhz",
-    "bls381_imad_peak_sustained",
+    "bls381_imad_peak_sustained", "bls381_set_option",
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
     "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
     "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_g1_scalar_mul_batch", "bls381_verify_batch_partial",
@@ -212,6 +213,10 @@ class Engine:
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.bls381_last_kernel_ms())
+
+    def set_option(self, name: str, value: int) -> None:
+        """engine tuning knob (see include/bls381_b200.h); never changes results"""
+        self._check(self.lib.bls381_set_option(name.encode(), int(value)))
 
     def last_kernel_sm_mhz(self) -> float:
         """effective SM clock during the last tower-VM launch (clock64 / globaltimer of CTA 0)"""

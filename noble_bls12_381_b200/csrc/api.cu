@@ -30,11 +30,13 @@ struct State {
     int device = -1;
     int sm_count = 0;
     std::map<std::string, Program> programs;
-    uint32_t* d_far = nullptr;
+    // far-slot scratch (global memory that stays in L2), ONE BUFFER PER STREAM: launches on different streams can overlap on
+    // the device (a persistent grid's tail), launches on one stream cannot
+    struct FarBuf { uint32_t* ptr = nullptr; size_t bytes = 0; };
+    std::map<cudaStream_t, FarBuf> far;
     static constexpr int kTickets = 4096;
     int dynamic_batches = 1;  // batches claimed from a global counter (+4.9 % at 65536 pairings, profiles/r1_notes.md)
     unsigned long long* d_clk = nullptr;  // clock probe of the last tower-VM launch {cycles, ns}
-    size_t far_bytes = 0;
     // grow-only device staging for the host entry points
     static constexpr int kStages = 10;
     uint8_t* d_stage[kStages] = {};
@@ -143,12 +145,22 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     if (g.force_ctas > 0) ctas_per_sm = std::min(ctas_per_sm, g.force_ctas);
     const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)(g.sm_count * ctas_per_sm));
     const size_t far_need = (size_t)grid * std::max<uint32_t>(p->nfar, 1) * vm::kSlotWords * 4;
-    if (far_need > g.far_bytes) {
-        if (g.d_far) cudaFree(g.d_far);
-        g.d_far = nullptr;
-        g.far_bytes = 0;
-        CUDA_TRY(cudaMalloc(&g.d_far, far_need));
-        g.far_bytes = far_need;
+    if (g.far.size() > 64 && !g.far.count(s)) {  // many short-lived caller streams: start over
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (auto& kv : g.far)
+            if (kv.second.ptr) cudaFree(kv.second.ptr);
+        g.far.clear();
+    }
+    State::FarBuf& fb = g.far[s];
+    if (far_need > fb.bytes) {
+        if (fb.ptr) {
+            CUDA_TRY(cudaStreamSynchronize(s));  // earlier launches on this stream may still use the old buffer
+            cudaFree(fb.ptr);
+        }
+        fb.ptr = nullptr;
+        fb.bytes = 0;
+        CUDA_TRY(cudaMalloc(&fb.ptr, far_need));
+        fb.bytes = far_need;
     }
     vm::Launch L;
     memset(&L, 0, sizeof(L));
@@ -160,7 +172,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     L.nfar = std::max<uint32_t>(p->nfar, 1);
     L.n_items = (uint32_t)n;
     L.pad = (uint32_t)g.sleep_ns;
-    L.far = g.d_far;
+    L.far = fb.ptr;
     for (int i = 0; i < nbuf; ++i) {
         L.buf[i].base = bufs[i];
         L.buf[i].stride = strides[i];
@@ -459,9 +471,9 @@ int bls381_shutdown(void) {
         cudaFree(kv.second.d_prog);
     }
     g.programs.clear();
-    if (g.d_far) cudaFree(g.d_far);
-    g.d_far = nullptr;
-    g.far_bytes = 0;
+    for (auto& kv : g.far)
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+    g.far.clear();
     if (g.d_clk) cudaFree(g.d_clk);
     g.d_clk = nullptr;
     for (int k = 0; k < State::kStages; ++k) {
@@ -483,6 +495,19 @@ const char* bls381_last_error(void) { return g_err.c_str(); }
 int bls381_sm_count(void) { return g.inited ? g.sm_count : 0; }
 uint64_t bls381_launch_count(void) { return g.launches.load(); }
 double bls381_last_kernel_ms(void) { return g.last_ms; }
+
+int bls381_set_option(const char* name, int value) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!name) return fail(BLS381_EINVAL, "null argument");
+    const std::string n(name);
+    if (n == "dynamic_batches") g.dynamic_batches = value != 0;
+    else if (n == "ctas_per_sm") g.force_ctas = value;
+    else if (n == "poll_sleep_ns") g.sleep_ns = value;
+    else if (n == "no_tma") g.no_tma = value != 0;
+    else return fail(BLS381_EINVAL, "unknown option: " + n);
+    return BLS381_OK;
+}
 
 double bls381_last_kernel_sm_mhz(void) {
     if (!g.inited || !g.d_clk) return 0.0;
