@@ -79,7 +79,7 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
     if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
-    if (p.nrec == 0 || p.nrec > 65535) return fail(BLS381_EPROGRAM, "record count out of range (16-bit progress counters): " + name);
+    if (p.nrec == 0 || p.nrec > 32767) return fail(BLS381_EPROGRAM, "record count out of range (15-bit progress counters): " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));

@@ -109,7 +109,28 @@ struct Ctx {
     const Buffer* buf;
     const uint8_t* stage;    // shared-memory staging area filled by TMA (nullptr in the CPU emulation)
     const uint32_t* stage_off;
+    // device only: 32-bit shared-window addresses, computed ONCE per thread (the generic-pointer path re-derives the
+    // shared window base with S2UR/ULEA and re-reads SR_TID before every access, ~5 % of the warp time in the v7 profile)
+    uint32_t sbase;          // &slots[0] + lane * 16
+    uint32_t cbase;          // &consts[0]
 };
+
+#if !defined(BLS381_CACHED_SMEM)
+#define BLS381_CACHED_SMEM 1
+#endif
+#if defined(__CUDA_ARCH__) && BLS381_CACHED_SMEM
+#define VM_SMEM_ASM 1
+#else
+#define VM_SMEM_ASM 0
+#endif
+#if defined(__CUDA_ARCH__)
+FPC_DEV void lds128(uint32_t* r, uint32_t addr) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+FPC_DEV void sts128(uint32_t addr, const uint32_t* r) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+#endif
 
 // start of this lane's record in input buffer `bufid` (TMA-staged copy in shared memory when available)
 FPC_DEV const uint8_t* wire_record(const Ctx& c, uint32_t bufid) {
@@ -127,37 +148,21 @@ FPC_DEV uint32_t bswap32(uint32_t v) {
 #endif
 }
 
-FPC_DEV void load_slot(uint32_t* r, const Ctx& c, uint32_t slot, uint32_t lane) {
-    if (slot < c.nslots) {
-        const uint32_t* s = c.slots + slot * kSlotWords + lane * 4;
+// r = 12 limbs of lane `lane`'s column of a slot given by pointer (generic-pointer path: far slots, builds without VM_SMEM_ASM)
+FPC_DEV void load_col(uint32_t* r, const uint32_t* s) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
-            r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-        }
-#else
-        for (int q = 0; q < 3; ++q)
-            for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
-#endif
-    } else {
-        const uint32_t* s = c.far + (slot - c.nslots) * kSlotWords + lane * 4;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
-            r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-        }
-#else
-        for (int q = 0; q < 3; ++q)
-            for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
-#endif
+    for (int q = 0; q < 3; ++q) {
+        uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
+        r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
     }
+#else
+    for (int q = 0; q < 3; ++q)
+        for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
+#endif
 }
 
-FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
-    uint32_t* s = (slot < c.nslots) ? c.slots + slot * kSlotWords + c.lane * 4
-                                    : c.far + (slot - c.nslots) * kSlotWords + c.lane * 4;
+FPC_DEV void store_col(uint32_t* s, const uint32_t* r) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int q = 0; q < 3; ++q)
@@ -166,6 +171,34 @@ FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
     for (int q = 0; q < 3; ++q)
         for (int k = 0; k < 4; ++k) s[q * 128 + k] = r[4 * q + k];
 #endif
+}
+
+FPC_DEV void load_slot(uint32_t* r, const Ctx& c, uint32_t slot, uint32_t lane) {
+    if (slot < c.nslots) {
+#if VM_SMEM_ASM
+        const uint32_t a = c.sbase + slot * (kSlotWords * 4u) + (lane - c.lane) * 16u;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) lds128(r + 4 * q, a + q * 512u);
+#else
+        load_col(r, c.slots + slot * kSlotWords + lane * 4);
+#endif
+    } else {
+        load_col(r, c.far + (slot - c.nslots) * kSlotWords + lane * 4);
+    }
+}
+
+FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
+    if (slot < c.nslots) {
+#if VM_SMEM_ASM
+        const uint32_t a = c.sbase + slot * (kSlotWords * 4u);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) sts128(a + q * 512u, r + 4 * q);
+#else
+        store_col(c.slots + slot * kSlotWords + c.lane * 4, r);
+#endif
+    } else {
+        store_col(c.far + (slot - c.nslots) * kSlotWords + c.lane * 4, r);
+    }
 }
 
 // wire format: big-endian field (48 or 32 bytes) at byte offset 16*off16 -> 12 little-endian limbs
@@ -207,25 +240,27 @@ FPC_DEV void scale_raw(uint32_t* v, int k) {
 
 FPC_DEV void load_one(uint32_t* r, const Ctx& c, uint32_t idx, uint32_t flags, uint32_t xmask) {
     if (flags & F_CONST) {
+#if VM_SMEM_ASM
+        const uint32_t a = c.cbase + idx * 48u;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) lds128(r + 4 * q, a + q * 16u);
+#else
         const uint32_t* s = c.consts + idx * 12;
 #pragma unroll
         for (int k = 0; k < 12; ++k) r[k] = s[k];
+#endif
     } else {
         load_slot(r, c, idx, (flags & F_XLANE) ? (c.lane ^ xmask) : c.lane);
     }
 }
 
 FPC_DEV void load_near(uint32_t* r, const Ctx& c, uint32_t slot) {
-    const uint32_t* s = c.slots + slot * kSlotWords + c.lane * 4;
-#if defined(__CUDA_ARCH__)
+#if VM_SMEM_ASM
+    const uint32_t a = c.sbase + slot * (kSlotWords * 4u);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        uint4 v = *reinterpret_cast<const uint4*>(s + q * 128);
-        r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-    }
+    for (int q = 0; q < 3; ++q) lds128(r + 4 * q, a + q * 512u);
 #else
-    for (int q = 0; q < 3; ++q)
-        for (int k = 0; k < 4; ++k) r[4 * q + k] = s[q * 128 + k];
+    load_col(r, c.slots + slot * kSlotWords + c.lane * 4);
 #endif
 }
 

@@ -2,6 +2,10 @@
 #include <cuda_runtime.h>
 #include "vm.cuh"
 
+#if !defined(BLS381_PACKED_PROGRESS)
+#define BLS381_PACKED_PROGRESS 0
+#endif
+
 namespace vm {
 
 __device__ __forceinline__ void wait_progress(const volatile uint32_t* progress, uint32_t w, uint32_t need, uint32_t sleep_ns) {
@@ -9,6 +13,18 @@ __device__ __forceinline__ void wait_progress(const volatile uint32_t* progress,
     while (progress[w] < need) {
         if (sleep_ns) __nanosleep(sleep_ns);  // back off: a spinning warp steals issue slots and LDS bandwidth
     }
+}
+
+// Packed progress counters (WARPS <= 8): eight 16-bit counters in ONE 16-byte shared-memory word, warp w at halfword w,
+// i.e. exactly the layout of the four requirement words of a record.  One LDS.128 + a borrow-free per-halfword compare
+// replaces eight dependent LDS/compare/branch rounds (~500 cycles per record even when nothing has to wait).
+// Counters and requirements are < 0x8000, so ((p | 0x8000) - q) has bit 15 set iff p >= q and never borrows across halves.
+__device__ __forceinline__ bool progress_reached(uint32_t paddr, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+    uint32_t p0, p1, p2, p3;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p0), "=r"(p1), "=r"(p2), "=r"(p3) : "r"(paddr) : "memory");
+    const uint32_t m = 0x80008000u;
+    const uint32_t ok = ((p0 | m) - q0) & ((p1 | m) - q1) & ((p2 | m) - q2) & ((p3 | m) - q3) & m;
+    return ok == m;
 }
 
 // Persistent CTAs: each CTA loops over batches of 32 items (lane = item).  Inside a batch there are NO
@@ -45,6 +61,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
     Ctx c;
     c.slots = slots;
     c.consts = sconst;
+    {   // 32-bit shared-window addresses held in registers (opaque to the compiler, so they are not re-derived per access)
+        const uint32_t sb = (uint32_t)__cvta_generic_to_shared(slots) + lane * 16u;
+        const uint32_t cb = (uint32_t)__cvta_generic_to_shared(sconst);
+        asm volatile("mov.u32 %0, %1;" : "=r"(c.sbase) : "r"(sb));
+        asm volatile("mov.u32 %0, %1;" : "=r"(c.cbase) : "r"(cb));
+    }
+    uint32_t paddr;  // packed 16-bit progress counters (first 16 bytes of the progress area)
+    {
+        const uint32_t pa = (uint32_t)__cvta_generic_to_shared(const_cast<uint32_t*>(progress));
+        asm volatile("mov.u32 %0, %1;" : "=r"(paddr) : "r"(pa));
+    }
     c.far = L.far + (size_t)blockIdx.x * L.nfar * kSlotWords;
     c.nslots = L.nslots;
     c.lane = lane;
@@ -122,7 +149,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
             if (hdr & H_BAR) {  // this record carries progress requirements
                 const uint32_t q0 = __shfl_sync(0xffffffffu, cur, 27), q1 = __shfl_sync(0xffffffffu, cur, 29);
                 const uint32_t q2 = __shfl_sync(0xffffffffu, cur, 30), q3 = __shfl_sync(0xffffffffu, cur, 31);
-                if (WARPS <= 8) {  // eight 16-bit fields
+                if (WARPS <= 8 && BLS381_PACKED_PROGRESS) {  // eight 16-bit fields, checked with one 128-bit load
+                    while (!progress_reached(paddr, q0, q1, q2, q3)) {
+                        if (L.pad) __nanosleep(L.pad);
+                    }
+                } else if (WARPS <= 8) {  // eight 16-bit fields, one 32-bit counter per warp
                     wait_progress(progress, 0, q0 & 0xFFFF, L.pad); wait_progress(progress, 1, q0 >> 16, L.pad);
                     wait_progress(progress, 2, q1 & 0xFFFF, L.pad); wait_progress(progress, 3, q1 >> 16, L.pad);
                     wait_progress(progress, 4, q2 & 0xFFFF, L.pad); wait_progress(progress, 5, q2 >> 16, L.pad);
@@ -152,7 +183,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
-                progress[warp] = r + 1;
+                if (WARPS <= 8 && BLS381_PACKED_PROGRESS) asm volatile("st.volatile.shared.u16 [%0], %1;" ::"r"(paddr + 2u * warp), "h"((unsigned short)(r + 1)) : "memory");
+                else progress[warp] = r + 1;
                 if (tracing) {
                     uint32_t* tp = L.trace + (((size_t)blockIdx.x * WARPS + warp) * L.nrec + r) * 8;
                     tp[0] = t0; tp[1] = t1; tp[2] = (uint32_t)clock64();
