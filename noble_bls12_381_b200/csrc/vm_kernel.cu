@@ -1,5 +1,6 @@
 // Tower-VM interpreter kernel for sm_100a.  See vm.cuh for the execution model.
 #include <cuda_runtime.h>
+#include <cstdio>
 #include "vm.cuh"
 
 #if !defined(BLS381_PACKED_PROGRESS)
@@ -15,16 +16,18 @@ __device__ __forceinline__ void wait_progress(const volatile uint32_t* progress,
     }
 }
 
-// Packed progress counters (WARPS <= 8): eight 16-bit counters in ONE 16-byte shared-memory word, warp w at halfword w,
-// i.e. exactly the layout of the four requirement words of a record.  One LDS.128 + a borrow-free per-halfword compare
-// replaces eight dependent LDS/compare/branch rounds (~500 cycles per record even when nothing has to wait).
+// Packed progress counters (WARPS <= 8): eight 16-bit counters in 16 bytes of shared memory, warp w at halfword w,
+// i.e. exactly the layout of the four requirement words of a record.  Lane l reads word (l & 3) with ONE LDS.32 (a single
+// shared-memory wavefront per poll, like the scalar loop) and compares both halves at once; a warp vote combines the four
+// words.  This replaces eight dependent LDS/compare/branch rounds (~500 cycles per record even when nothing has to wait).
 // Counters and requirements are < 0x8000, so ((p | 0x8000) - q) has bit 15 set iff p >= q and never borrows across halves.
-__device__ __forceinline__ bool progress_reached(uint32_t paddr, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
-    uint32_t p0, p1, p2, p3;
-    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p0), "=r"(p1), "=r"(p2), "=r"(p3) : "r"(paddr) : "memory");
+// (An LDS.128 per lane was tried first: four wavefronts per poll saturate the shared-memory pipe when many warps spin and
+// the producers' stores starve -- the kernel live-locks.)
+__device__ __forceinline__ bool progress_reached(uint32_t paddr_lane, uint32_t q) {
+    uint32_t p;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(p) : "r"(paddr_lane) : "memory");
     const uint32_t m = 0x80008000u;
-    const uint32_t ok = ((p0 | m) - q0) & ((p1 | m) - q1) & ((p2 | m) - q2) & ((p3 | m) - q3) & m;
-    return ok == m;
+    return __all_sync(0xffffffffu, (((p | m) - q) & m) == m);
 }
 
 // Persistent CTAs: each CTA loops over batches of 32 items (lane = item).  Inside a batch there are NO
@@ -67,11 +70,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
         asm volatile("mov.u32 %0, %1;" : "=r"(c.sbase) : "r"(sb));
         asm volatile("mov.u32 %0, %1;" : "=r"(c.cbase) : "r"(cb));
     }
-    uint32_t paddr;  // packed 16-bit progress counters (first 16 bytes of the progress area)
+    uint32_t paddr, paddr_lane;  // packed 16-bit progress counters (first 16 bytes of the progress area); this lane's word
     {
         const uint32_t pa = (uint32_t)__cvta_generic_to_shared(const_cast<uint32_t*>(progress));
         asm volatile("mov.u32 %0, %1;" : "=r"(paddr) : "r"(pa));
+        asm volatile("mov.u32 %0, %1;" : "=r"(paddr_lane) : "r"(pa + (lane & 3u) * 4u));
     }
+    const uint32_t qidx = 27u + (lane & 3u) + ((lane & 3u) ? 1u : 0u);  // requirement words 27, 29, 30, 31
     c.far = L.far + (size_t)blockIdx.x * L.nfar * kSlotWords;
     c.nslots = L.nslots;
     c.lane = lane;
@@ -147,18 +152,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
             const uint32_t hdr = __shfl_sync(0xffffffffu, cur, 0);
             const uint32_t aux = __shfl_sync(0xffffffffu, cur, 1);
             if (hdr & H_BAR) {  // this record carries progress requirements
-                const uint32_t q0 = __shfl_sync(0xffffffffu, cur, 27), q1 = __shfl_sync(0xffffffffu, cur, 29);
-                const uint32_t q2 = __shfl_sync(0xffffffffu, cur, 30), q3 = __shfl_sync(0xffffffffu, cur, 31);
-                if (WARPS <= 8 && BLS381_PACKED_PROGRESS) {  // eight 16-bit fields, checked with one 128-bit load
-                    while (!progress_reached(paddr, q0, q1, q2, q3)) {
+                if (WARPS <= 8 && BLS381_PACKED_PROGRESS) {  // eight 16-bit fields: one LDS.32 per lane + a vote
+                    const uint32_t q = __shfl_sync(0xffffffffu, cur, qidx);
+#if defined(BLS381_PROGRESS_DEBUG)
+                    unsigned long long spins = 0;
+#endif
+                    while (!progress_reached(paddr_lane, q)) {
                         if (L.pad) __nanosleep(L.pad);
+#if defined(BLS381_PROGRESS_DEBUG)   // watchdog (debug builds): report the stuck wait and carry on
+                        if (++spins > 20000000ull) {
+                            if (lane < 4) printf("STUCK cta %u warp %u rec %u lane %u q=%08x\n", blockIdx.x, warp, r, lane, q);
+                            break;
+                        }
+#endif
                     }
                 } else if (WARPS <= 8) {  // eight 16-bit fields, one 32-bit counter per warp
+                    const uint32_t q0 = __shfl_sync(0xffffffffu, cur, 27), q1 = __shfl_sync(0xffffffffu, cur, 29);
+                    const uint32_t q2 = __shfl_sync(0xffffffffu, cur, 30), q3 = __shfl_sync(0xffffffffu, cur, 31);
                     wait_progress(progress, 0, q0 & 0xFFFF, L.pad); wait_progress(progress, 1, q0 >> 16, L.pad);
                     wait_progress(progress, 2, q1 & 0xFFFF, L.pad); wait_progress(progress, 3, q1 >> 16, L.pad);
                     wait_progress(progress, 4, q2 & 0xFFFF, L.pad); wait_progress(progress, 5, q2 >> 16, L.pad);
                     wait_progress(progress, 6, q3 & 0xFFFF, L.pad); wait_progress(progress, 7, q3 >> 16, L.pad);
                 } else {           // ten 12-bit fields packed little-endian over the four words
+                    const uint32_t q0 = __shfl_sync(0xffffffffu, cur, 27), q1 = __shfl_sync(0xffffffffu, cur, 29);
+                    const uint32_t q2 = __shfl_sync(0xffffffffu, cur, 30), q3 = __shfl_sync(0xffffffffu, cur, 31);
                     const uint64_t lo = ((uint64_t)q1 << 32) | q0, hi = ((uint64_t)q3 << 32) | q2;
 #pragma unroll
                     for (int k = 0; k < WARPS && k < 10; ++k) {

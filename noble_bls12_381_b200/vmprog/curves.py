@@ -170,20 +170,32 @@ class Curve:
                 acc = self.add(acc, p)
         return acc
 
-    def mul_secret(self, p, nbits: int, bit_fn):
-        """[k]P for a per-lane secret k: always double, always add, select on bit i (MSB first).  `bit_fn(i)`
-        creates the flag for bit i; it is fenced behind the previous iteration so that the 255 flags are
-        produced just in time instead of occupying slots from the start of the program."""
+    def mul_secret(self, p, nbits: int, bit_fn, window: int = 4):
+        """[k]P for a per-lane secret k < 2^nbits, constant-time: fixed windows of `window` bits, a table of
+        0*P .. (2^w - 1)*P, per digit `window` doublings, a select tree over the digit's bit flags (every lane
+        touches every table entry) and ONE complete addition.  The reference's ladder (math.ts:1061-1078) does a
+        double and an add per bit; the group element -- hence every serialised byte -- is the same.
+        `bit_fn(i)` creates the flag for bit i (MSB first); it is fenced behind the previous digit so that the
+        flags are produced just in time instead of occupying slots from the start of the program."""
         F, b = self.F, self.b
-        acc = self._mat_point((F.zero(), F.one(), F.zero()))
-        for i in range(nbits - 1, -1, -1):
-            acc = self.dbl(acc)
-            fence = [c.t and list(c.t)[0].op for c in F.coeffs(acc[0]) if isinstance(c, Lin) and c.t]
-            b.set_after([op for op in fence if op is not None])
-            flag = bit_fn(i)
+        p = self._mat_point(p)
+        tab = [self._mat_point((F.zero(), F.one(), F.zero())), p]
+        for k in range(2, 1 << window):
+            tab.append(self.dbl(tab[k // 2]) if k % 2 == 0 else self.add(tab[k - 1], p))
+        ndig = (nbits + window - 1) // window
+        acc = None
+        for d in range(ndig - 1, -1, -1):
+            if acc is not None:
+                for _ in range(window):
+                    acc = self.dbl(acc)
+                fence = [c.t and list(c.t)[0].op for c in F.coeffs(acc[0]) if isinstance(c, Lin) and c.t]
+                b.set_after([op for op in fence if op is not None])
+            flags = [bit_fn(window * d + i) for i in range(window)]
             b.set_after([])
-            t = self.add(acc, p)
-            acc = tuple(F.select(flag, tc, ac) for tc, ac in zip(t, acc))
+            level = tab
+            for f in flags:  # bit i of the digit halves the candidate list
+                level = [tuple(F.select(f, hi, lo) for hi, lo in zip(level[2 * j + 1], level[2 * j])) for j in range(len(level) // 2)]
+            acc = level[0] if acc is None else self.add(acc, level[0])
         return acc
 
     def _mat_point(self, p):
@@ -261,9 +273,38 @@ class Ingest:
         return pow_fixed(lambda x, y: x * y, lambda x: x * x, lambda q: Lin.of(b.mat(q)), self.t.fp_const(1), a, (P + 1) // 4)
 
     def fp2_pow(self, a: E2, e: int) -> E2:
+        """a^e in Fp2 for a public exponent.  Exponents longer than p are split with the Frobenius map:
+        e = e1*p + e0 and a^p = conj(a) (math.ts:529-531), so a^e = conj(a)^e1 * a^e0 is ONE joint
+        double-base chain over 2-bit digit pairs -- half the squarings of the plain 758-bit chains the
+        reference runs for (p^2-9)/16 and (p^2+8)/16 (math.ts:1200, 489); same field element, same bytes."""
         b = self.b
         a = a.m(b)
-        return pow_fixed(lambda x, y: x * y, lambda x: x.sqr(), lambda q: q.m(b), self.F2.one(), a, e)
+        if e.bit_length() <= P.bit_length():
+            return pow_fixed(lambda x, y: x * y, lambda x: x.sqr(), lambda q: q.m(b), self.F2.one(), a, e)
+        e1, e0 = divmod(e, P)
+        assert e1 < P
+        pw = [None, a, a.sqr().m(b)]
+        pw.append((pw[2] * a).m(b))
+        tab = {}  # (i, j) -> a^i * conj(a)^j
+        for i in range(4):
+            for j in range(4):
+                if i == 0 and j == 0:
+                    continue
+                if j == 0:
+                    tab[(i, j)] = pw[i]
+                elif i == 0:
+                    tab[(i, j)] = pw[j].conj()
+                else:
+                    tab[(i, j)] = (pw[i] * pw[j].conj()).m(b)
+        ndig = (max(e0.bit_length(), e1.bit_length()) + 1) // 2
+        acc = None
+        for d in range(ndig - 1, -1, -1):
+            i, j = (e0 >> (2 * d)) & 3, (e1 >> (2 * d)) & 3
+            if acc is not None:
+                acc = acc.sqr().m(b).sqr().m(b)
+            if i or j:
+                acc = tab[(i, j)] if acc is None else (acc * tab[(i, j)]).m(b)
+        return acc
 
     def fp2_eq(self, a: E2, c: E2) -> Val:
         return self.F2.is_zero(a - c)

@@ -116,3 +116,68 @@ def test_hash_to_g2_program():
     for i, m in enumerate(msgs):
         (x0, x1), (y0, y1) = O.pt_to_affine(O.G2, O.g2_hash_to_curve(m))
         assert bytes(out[192 * i : 192 * i + 192]) == b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1)), i
+
+
+def _scalars():
+    rng = random.Random(11)
+    r = O.R_ORDER
+    return [1, 2, 15, 16, 17, r - 1, r, (1 << 254) + 1, (1 << 255) - 19 if (1 << 255) - 19 <= r else r - 2, 0xF0F0F0F0 << 200] + \
+        [rng.randrange(1, r) for _ in range(4)]
+
+
+def test_g2_scalar_mul_program_windowed():
+    """Fixed-window constant-time scalar multiplication vs the oracle's ladder (math.ts:1061-1078), edge scalars."""
+    b = vmcompile.compile_program("g2_scalar_mul")
+    ks = _scalars()
+    n = len(ks)
+    q = O.pt_to_affine(O.G2, O.pt_multiply_unsafe(O.G2, O.G2_BASE, 0xC0FFEE))
+    qb = b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+    out, st = bytearray(192 * n), bytearray(4 * n)
+    emu.run_program(b, {0: (bytearray(qb * n), 192), 1: (bytearray(b"".join(k.to_bytes(32, "big") for k in ks)), 32),
+                        2: (out, 192), 5: (st, 4)}, n)
+    status = struct.unpack("<%di" % n, st)
+    qp = (q[0], q[1], O.FP2_ONE)
+    for i, k in enumerate(ks):
+        e = O.pt_multiply_unsafe(O.G2, qp, k)
+        if O.pt_is_zero(O.G2, e):
+            assert status[i] == 2, i
+            continue
+        (x0, x1), (y0, y1) = O.pt_to_affine(O.G2, e)
+        assert status[i] == 0, i
+        assert bytes(out[192 * i : 192 * i + 192]) == b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1)), i
+
+
+def test_g1_scalar_mul_program_windowed():
+    b = vmcompile.compile_program("g1_scalar_mul")
+    ks = _scalars()
+    n = len(ks)
+    q = O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, 0xBEEF))
+    qb = q[0].to_bytes(48, "big") + q[1].to_bytes(48, "big")
+    out, st = bytearray(96 * n), bytearray(4 * n)
+    emu.run_program(b, {0: (bytearray(qb * n), 96), 1: (bytearray(b"".join(k.to_bytes(32, "big") for k in ks)), 32),
+                        2: (out, 96), 5: (st, 4)}, n)
+    status = struct.unpack("<%di" % n, st)
+    for i, k in enumerate(ks):
+        e = O.pt_multiply_unsafe(O.G1, (q[0], q[1], 1), k)
+        if O.pt_is_zero(O.G1, e):
+            assert status[i] == 2, i
+            continue
+        x, y = O.pt_to_affine(O.G1, e)
+        assert status[i] == 0, i
+        assert bytes(out[96 * i : 96 * i + 96]) == x.to_bytes(48, "big") + y.to_bytes(48, "big"), i
+
+
+def test_sign_program_against_reference_kats():
+    """sign = hash-to-curve + windowed sk*H(m) + compression, on the first reference KATs (index.test.ts:287-293)."""
+    lines = [l.split(":") for l in open(os.path.join(GOLDEN, "sign_g2_vectors.txt")).read().split("\n") if l][:6]
+    b = vmcompile.compile_program("sign")
+    n = len(lines)
+    xmd = bytearray(b"".join(O.expand_message_xmd(bytes.fromhex(m), O.DEFAULT_DST, 256) for _, m, _ in lines))
+    sks = bytearray(b"".join((int(sk, 16) % O.R_ORDER).to_bytes(32, "big") for sk, _, _ in lines))
+    out, fl = bytearray(96 * n), bytearray(4 * n)
+    emu.run_program(b, {0: (xmd, 256), 1: (sks, 32), 2: (out, 96), 5: (fl, 4)}, n)
+    flags = struct.unpack("<%di" % n, fl)
+    for i, (_, _, sig) in enumerate(lines):
+        body = bytearray(out[96 * i : 96 * i + 96])
+        body[0] |= 0x80 | (0x40 if flags[i] & 2 else 0) | (0x20 if flags[i] & 1 else 0)
+        assert bytes(body).hex() == sig.strip().lower(), i
