@@ -163,7 +163,7 @@ def verify_section(eng, n, rank, world, dist, torch):
     P_ = synth.P
     # keys sk_i = i + 1 on every rank (public keys (i+1)*G1 from the host-side synthetic generator); the messages
     # are distinct per (rank, i), so the world x n batch has world x n different (message, signature) pairs
-    g1, _ = synth.multiples_wire(n)
+    g1 = synth.g1_multiples_wire(n)
     pks = []
     for i in range(n):
         x = int.from_bytes(g1[96 * i: 96 * i + 48], "big")
@@ -263,7 +263,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--program-dir", default=None, help="alternative tower-VM program directory (tuning)")
     ap.add_argument("--wide-per-product", type=int, default=144, help="IMAD.WIDE per 384x384 product of the built Fp core (108 for -DBLS381_KARATSUBA)")
-    ap.add_argument("--verify-n", type=int, default=65536, help="signatures per GPU for the verifyBatch / sign section (0 = skip)")
+    ap.add_argument("--verify-n", type=int, default=262144, help="signatures per GPU for the verifyBatch / sign section: BASELINE config 3 (262 144 on one GPU; x8 GPUs = config 5); 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -49,6 +49,7 @@ struct State {
     int force_ctas = 0;  // tuning override (env BLS381_B200_CTAS)
     int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
+    int pairs_per_lane = 2;  // Miller-product lanes handle 2 items with shared squarings (env BLS381_B200_PAIRS_PER_LANE=1: one)
 };
 
 State g;
@@ -136,13 +137,14 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     int rc = get_program(name, &p);
     if (rc) return rc;
     const uint32_t nbatch = (uint32_t)((n + 31) / 32);
-    size_t stage_est = 0;
-    for (int i = 0; i < nbuf; ++i)
-        if ((p->staged_mask >> i & 1) && strides[i]) stage_est += 32u * strides[i];
-    const size_t smem_est = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 16 + std::min<size_t>(stage_est, 20480) + 1024;
+    // CTAs per SM from the program's own shared memory (slots + constants + progress + mbarrier); the TMA staging of the
+    // wire-format inputs then only takes what is left of an SM's share, so that staging never costs a resident CTA
+    const size_t smem_base = (size_t)p->nslots * vm::kSlotWords * 4 + (size_t)p->nconst * 48 + 64 + 16;
     const int max_ctas = p->warps == 2 ? 8 : (p->warps == 4 ? 4 : (p->warps == 6 ? 3 : 2));
-    int ctas_per_sm = std::max(1, std::min(max_ctas, (int)(232448 / smem_est)));
+    int ctas_per_sm = std::max(1, std::min(max_ctas, (int)(232448 / (smem_base + 1024))));
     if (g.force_ctas > 0) ctas_per_sm = std::min(ctas_per_sm, g.force_ctas);
+    const size_t per_cta = 232448 / (size_t)ctas_per_sm;
+    const size_t stage_budget = std::min<size_t>(per_cta > smem_base + 1024 ? per_cta - smem_base - 1024 : 0, 20480) & ~(size_t)15;
     const int grid = (int)std::min<uint32_t>(nbatch, (uint32_t)(g.sm_count * ctas_per_sm));
     const size_t far_need = (size_t)grid * std::max<uint32_t>(p->nfar, 1) * vm::kSlotWords * 4;
     if (g.far.size() > 64 && !g.far.count(s)) {  // many short-lived caller streams: start over
@@ -183,7 +185,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     for (int i = 0; i < vm::kMaxBuffers; ++i) {
         L.stage_off[i] = vm::kNoStage;
         if (!g.no_tma && i < nbuf && (p->staged_mask >> i & 1) && bufs[i] && strides[i] && strides[i] % 16 == 0 &&
-            reinterpret_cast<uintptr_t>(bufs[i]) % 16 == 0 && stage_bytes + 32u * strides[i] <= 20480) {
+            reinterpret_cast<uintptr_t>(bufs[i]) % 16 == 0 && stage_bytes + 32u * strides[i] <= stage_budget) {
             L.stage_off[i] = stage_bytes;
             stage_bytes += 32u * strides[i];
         }
@@ -272,13 +274,23 @@ int product_tree(uint8_t* d_a, size_t count, uint8_t* d_b, uint8_t** result, cud
 
 int miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int fe, uint8_t* d_out, cudaStream_t s) {
     if (n == 0) return fail(BLS381_EINVAL, "empty batch");
-    const size_t nb = (n + 31) / 32;
+    // Two consecutive items per lane share the Fp12 squarings of the Miller loop (program miller_product2: the product of
+    // the individual Miller loops, bit for bit); an odd last item goes through the one-pair program.
+    const size_t n2 = g.pairs_per_lane >= 2 ? n / 2 : 0, n1 = n - 2 * n2;
+    const size_t nb2 = (n2 + 31) / 32, nb1 = (n1 + 31) / 32, nb = nb2 + nb1;
     int rc;
     if ((rc = stage(2, nb * 576))) return rc;
     if ((rc = stage(3, ((nb + 31) / 32) * 576 + 576))) return rc;
-    uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1), const_cast<uint8_t*>(d_g2), g.d_stage[2]};
-    uint32_t strides[3] = {96, 192, 576};
-    if ((rc = vm_run("miller_product", bufs, strides, 3, n, s))) return rc;
+    if (n2) {
+        uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1), const_cast<uint8_t*>(d_g2), g.d_stage[2]};
+        uint32_t strides[3] = {192, 384, 576};
+        if ((rc = vm_run("miller_product2", bufs, strides, 3, n2, s))) return rc;
+    }
+    if (n1) {
+        uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1) + 2 * n2 * 96, const_cast<uint8_t*>(d_g2) + 2 * n2 * 192, g.d_stage[2] + nb2 * 576};
+        uint32_t strides[3] = {96, 192, 576};
+        if ((rc = vm_run("miller_product", bufs, strides, 3, n1, s))) return rc;
+    }
     uint8_t* res = nullptr;
     if ((rc = product_tree(g.d_stage[2], nb, g.d_stage[3], &res, s))) return rc;
     if (fe) {
@@ -449,6 +461,7 @@ int bls381_init(int device, const char* program_dir) {
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
+    if (const char* e = getenv("BLS381_B200_PAIRS_PER_LANE")) g.pairs_per_lane = atoi(e);
     if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
     CUDA_TRY(cudaMalloc(&g.d_clk, 16 + 4 * State::kTickets));  // {cycles, ns} clock probe + batch ticket counters
     CUDA_TRY(cudaMemset(g.d_clk, 0, 16 + 4 * State::kTickets));
@@ -505,6 +518,7 @@ int bls381_set_option(const char* name, int value) {
     else if (n == "ctas_per_sm") g.force_ctas = value;
     else if (n == "poll_sleep_ns") g.sleep_ns = value;
     else if (n == "no_tma") g.no_tma = value != 0;
+    else if (n == "pairs_per_lane") g.pairs_per_lane = value;
     else return fail(BLS381_EINVAL, "unknown option: " + n);
     return BLS381_OK;
 }

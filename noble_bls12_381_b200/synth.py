@@ -98,3 +98,9 @@ def multiples_wire(n: int):
     b1 = b"".join(x.to_bytes(48, "big") + y.to_bytes(48, "big") for x, y in g1)
     b2 = b"".join(b"".join(c.to_bytes(48, "big") for c in (x[0], x[1], y[0], y[1])) for x, y in g2)
     return b1, b2
+
+
+def g1_multiples_wire(n: int):
+    """g1_bytes n x 96 for i*G1, i = 1..n (the public keys of the secret keys 1..n)."""
+    g1 = _multiples(_F1, (GX, GY), n, 3)
+    return b"".join(x.to_bytes(48, "big") + y.to_bytes(48, "big") for x, y in g1)

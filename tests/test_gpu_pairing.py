@@ -106,6 +106,22 @@ def test_miller_product_tree(eng, O, n):
         assert fe == O.fp12_to_bytes(O.fp12_final_exponentiate(acc))
 
 
+def test_pairs_per_lane_is_result_neutral(eng):
+    """The two-items-per-lane Miller product (shared Fp12 squarings) and the one-item-per-lane program give the same raw
+    (unexponentiated) product bytes for even, odd and multi-level-tree sizes."""
+    from noble_bls12_381_b200 import synth
+    g1, g2 = synth.multiples_wire(2051)
+    try:
+        for n in (2, 3, 64, 65, 2050, 2051):
+            eng.set_option("pairs_per_lane", 1)
+            one = eng.miller_product(g1[: 96 * n], g2[: 192 * n], n, False)
+            eng.set_option("pairs_per_lane", 2)
+            two = eng.miller_product(g1[: 96 * n], g2[: 192 * n], n, False)
+            assert one == two, n
+    finally:
+        eng.set_option("pairs_per_lane", 2)
+
+
 def test_bilinearity_at_scale(eng, O):
     """Size-independent property at a large batch: e(a_i*G1, G2) * e(-G1, a_i*G2) == 1 for every i, checked
     through the multi-Miller product + one final exponentiation == ONE, plus e(P,Q)^r == 1 spot checks."""
