@@ -141,8 +141,8 @@ int bls381_vm_load(const char* name, const uint8_t* image, size_t len);
 
 /* Engine tuning knobs (same as the BLS381_B200_* environment variables read by bls381_init): "dynamic_batches" (1 = CTAs
  * claim 32-item batches from a global counter, 0 = round-robin), "ctas_per_sm" (0 = automatic), "poll_sleep_ns",
- * "no_tma" (1 = read wire-format inputs directly from global memory), "pairs_per_lane" (2 = the Miller-product entry
- * points give every lane two consecutive items that share the Fp12 squarings, 1 = one item per lane).
+ * "no_tma" (1 = read wire-format inputs directly from global memory), "pairs_per_lane" (1..4, default 3: the
+ * Miller-product entry points give every lane that many consecutive items, which share the Fp12 squarings).
  * Results never depend on them.                                                                                 */
 int bls381_set_option(const char* name, int value);
 

@@ -49,7 +49,9 @@ struct State {
     int force_ctas = 0;  // tuning override (env BLS381_B200_CTAS)
     int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
-    int pairs_per_lane = 2;  // Miller-product lanes handle 2 items with shared squarings (env BLS381_B200_PAIRS_PER_LANE=1: one)
+    // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
+    // verifyBatch at 131072 signatures on a B200: 1.26 / 1.39 / 1.42 / 1.40 M sigs/s for 1 / 2 / 3 / 4
+    int pairs_per_lane = 3;
 };
 
 State g;
@@ -274,20 +276,22 @@ int product_tree(uint8_t* d_a, size_t count, uint8_t* d_b, uint8_t** result, cud
 
 int miller_product_dev(const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int fe, uint8_t* d_out, cudaStream_t s) {
     if (n == 0) return fail(BLS381_EINVAL, "empty batch");
-    // Two consecutive items per lane share the Fp12 squarings of the Miller loop (program miller_product2: the product of
-    // the individual Miller loops, bit for bit); an odd last item goes through the one-pair program.
-    const size_t n2 = g.pairs_per_lane >= 2 ? n / 2 : 0, n1 = n - 2 * n2;
-    const size_t nb2 = (n2 + 31) / 32, nb1 = (n1 + 31) / 32, nb = nb2 + nb1;
+    // k consecutive items per lane share the Fp12 squarings of the Miller loop (programs miller_product2/3/4: the product
+    // of the individual Miller loops, bit for bit); the n mod k last items go through the one-pair program.
+    const size_t k = (size_t)std::min(std::max(g.pairs_per_lane, 1), 4);
+    const size_t nk = k >= 2 ? n / k : 0, n1 = n - k * nk;
+    const size_t nbk = (nk + 31) / 32, nb1 = (n1 + 31) / 32, nb = nbk + nb1;
     int rc;
     if ((rc = stage(2, nb * 576))) return rc;
     if ((rc = stage(3, ((nb + 31) / 32) * 576 + 576))) return rc;
-    if (n2) {
+    if (nk) {
+        static const char* const kProg[5] = {nullptr, nullptr, "miller_product2", "miller_product3", "miller_product4"};
         uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1), const_cast<uint8_t*>(d_g2), g.d_stage[2]};
-        uint32_t strides[3] = {192, 384, 576};
-        if ((rc = vm_run("miller_product2", bufs, strides, 3, n2, s))) return rc;
+        uint32_t strides[3] = {(uint32_t)(96 * k), (uint32_t)(192 * k), 576};
+        if ((rc = vm_run(kProg[k], bufs, strides, 3, nk, s))) return rc;
     }
     if (n1) {
-        uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1) + 2 * n2 * 96, const_cast<uint8_t*>(d_g2) + 2 * n2 * 192, g.d_stage[2] + nb2 * 576};
+        uint8_t* bufs[3] = {const_cast<uint8_t*>(d_g1) + k * nk * 96, const_cast<uint8_t*>(d_g2) + k * nk * 192, g.d_stage[2] + nbk * 576};
         uint32_t strides[3] = {96, 192, 576};
         if ((rc = vm_run("miller_product", bufs, strides, 3, n1, s))) return rc;
     }

@@ -449,13 +449,14 @@ def build_miller_product(warps=6) -> Builder:
     return b
 
 
-def build_miller_product2(warps=6) -> Builder:
-    """One Fp12 per 32-lane batch, TWO pairs per lane: lane l of a batch handles the consecutive items 2l and 2l+1 (the
-    caller passes doubled strides: 192 B of G1 and 384 B of G2 per lane) and shares the Fp12 squarings between them."""
+def build_miller_product2(warps=6, per_lane=2) -> Builder:
+    """One Fp12 per 32-lane batch, `per_lane` pairs per lane: lane l of a batch handles the consecutive items
+    per_lane*l .. per_lane*l + per_lane - 1 (the caller passes multiplied strides: per_lane x 96 B of G1 and
+    per_lane x 192 B of G2 per lane) and shares the Fp12 squarings between them."""
     b = Builder(warps)
     t = Tower(b)
     pairs = []
-    for k in range(2):
+    for k in range(per_lane):
         Px = Lin.of(b.inp(BUF_G1, 2 * k))
         Py = Lin.of(b.inp(BUF_G1, 2 * k + 1))
         Qx = E2(Lin.of(b.inp(BUF_G2, 4 * k)), Lin.of(b.inp(BUF_G2, 4 * k + 1)))
@@ -484,6 +485,8 @@ PROGRAMS = {
     "final_exp": build_final_exp,
     "miller_product": build_miller_product,
     "miller_product2": build_miller_product2,
+    "miller_product3": lambda w: build_miller_product2(w, 3),
+    "miller_product4": lambda w: build_miller_product2(w, 4),
     "f12_product": build_f12_product,
     "f12_mul_test": build_fp12_mul_test,
 }

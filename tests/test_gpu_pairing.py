@@ -107,19 +107,19 @@ def test_miller_product_tree(eng, O, n):
 
 
 def test_pairs_per_lane_is_result_neutral(eng):
-    """The two-items-per-lane Miller product (shared Fp12 squarings) and the one-item-per-lane program give the same raw
-    (unexponentiated) product bytes for even, odd and multi-level-tree sizes."""
+    """The k-items-per-lane Miller products (shared Fp12 squarings, k = 2, 3, 4) and the one-item-per-lane program give
+    the same raw (unexponentiated) product bytes for sizes with every remainder and a multi-level product tree."""
     from noble_bls12_381_b200 import synth
-    g1, g2 = synth.multiples_wire(2051)
+    g1, g2 = synth.multiples_wire(3083)
     try:
-        for n in (2, 3, 64, 65, 2050, 2051):
-            eng.set_option("pairs_per_lane", 1)
-            one = eng.miller_product(g1[: 96 * n], g2[: 192 * n], n, False)
-            eng.set_option("pairs_per_lane", 2)
-            two = eng.miller_product(g1[: 96 * n], g2[: 192 * n], n, False)
-            assert one == two, n
+        for n in (2, 3, 4, 5, 64, 97, 3083):
+            outs = []
+            for k in (1, 2, 3, 4):
+                eng.set_option("pairs_per_lane", k)
+                outs.append(eng.miller_product(g1[: 96 * n], g2[: 192 * n], n, False))
+            assert outs[0] == outs[1] == outs[2] == outs[3], n
     finally:
-        eng.set_option("pairs_per_lane", 2)
+        eng.set_option("pairs_per_lane", 3)
 
 
 def test_bilinearity_at_scale(eng, O):

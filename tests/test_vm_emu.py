@@ -137,15 +137,16 @@ def test_product_tree_programs_on_emulator(programs):
     assert bytes(out) == O.fp12_to_bytes(prod(mill))
 
 
-def test_two_pairs_per_lane_miller_product_on_emulator():
-    """miller_product2: two consecutive items per lane with shared Fp12 squarings == product of the individual Miller
-    loops, bit for bit (raw, before any final exponentiation); 70 items = 35 lane-items = two batches, ragged."""
-    b = vmcompile.compile_program("miller_product2")
+@pytest.mark.parametrize("k", [2, 3])
+def test_pairs_per_lane_miller_product_on_emulator(k):
+    """miller_product<k>: k consecutive items per lane with shared Fp12 squarings == product of the individual Miller
+    loops, bit for bit (raw, before any final exponentiation); 35 lane-items = two batches, the second ragged."""
+    b = vmcompile.compile_program("miller_product%d" % k)
     b.check_hazards()
-    n = 70
+    n = 35 * k
     pts, g1, g2 = _random_pairs(n, 9)
     part = bytearray(576 * 2)
-    emu.run_program(b, {0: (g1, 192), 1: (g2, 384), 2: (part, 576)}, n // 2)
+    emu.run_program(b, {0: (g1, 96 * k), 1: (g2, 192 * k), 2: (part, 576)}, n // k)
     mill = [_miller(p, q) for p, q in pts]
 
     def prod(fs):
@@ -154,8 +155,8 @@ def test_two_pairs_per_lane_miller_product_on_emulator():
             r = O.fp12_mul(r, f)
         return r
 
-    assert bytes(part[:576]) == O.fp12_to_bytes(prod(mill[:64]))
-    assert bytes(part[576:]) == O.fp12_to_bytes(prod(mill[64:]))
+    assert bytes(part[:576]) == O.fp12_to_bytes(prod(mill[: 32 * k]))
+    assert bytes(part[576:]) == O.fp12_to_bytes(prod(mill[32 * k :]))
 
 
 def test_synth_matches_oracle_multiples():
