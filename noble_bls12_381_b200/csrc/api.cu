@@ -769,6 +769,48 @@ int bls381_verify_batch_partial(const uint8_t* sig96_or_null, const uint8_t* msg
     return verify_partial(sig96_or_null, msgs, msg_off, pks48, n, dst, dst_len, 0, out_fp12, status);
 }
 
+// sign: the secret scalar as four base-z digits (z = |x| = 0xd201000000010000; k < r < z^4), written in place as
+// a_3 || a_2 || a_1 || a_0 (8 bytes big-endian each), the input format of the `sign` program's joint ladder over
+// psi^i(H(m)) (vmprog/curves.py: g2_mul_secret_gls4).  Scalars >= r are reduced first ([k]P = [k mod r]P on G2).
+__global__ void base_z_digits_kernel(uint8_t* sk32, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t* p = sk32 + 32 * i;
+    unsigned long long w[4];  // w[3] most significant
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long v = 0;
+        for (int b = 0; b < 8; ++b) v = (v << 8) | p[8 * (3 - k) + b];
+        w[k] = v;
+    }
+    const unsigned long long r[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+    for (int rep = 0; rep < 3; ++rep) {  // k < 2^256 < 3r
+        bool ge = true;
+        for (int k = 3; k >= 0; --k) {
+            if (w[k] != r[k]) { ge = w[k] > r[k]; break; }
+        }
+        if (!ge) break;
+        unsigned long long borrow = 0;
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long a = w[k], s1 = a - r[k], s2 = s1 - borrow;
+            borrow = (a < r[k]) | (s1 < borrow);
+            w[k] = s2;
+        }
+    }
+    const unsigned long long z = 0xd201000000010000ull;
+    unsigned long long digit[4];
+    for (int d = 0; d < 4; ++d) {
+        unsigned long long rem = 0;
+        for (int k = 3; k >= 0; --k) {
+            const unsigned __int128 cur = ((unsigned __int128)rem << 64) | w[k];
+            w[k] = (unsigned long long)(cur / z);
+            rem = (unsigned long long)(cur % z);
+        }
+        digit[d] = rem;
+    }
+    for (int d = 0; d < 4; ++d)
+        for (int b = 0; b < 8; ++b) p[8 * (3 - d) + b] = (uint8_t)(digit[d] >> (8 * (7 - b)));
+}
+
 int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst,
                       size_t dst_len, uint8_t* out_sig96) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -790,6 +832,8 @@ int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t*
     CUDA_TRY(cudaEventRecord(g.ev0, s));
     xmd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, g.d_stage[5],
                                                        (uint32_t)dp.size(), g.d_stage[4]);
+    CUDA_TRY(cudaGetLastError());
+    base_z_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[7], n);
     CUDA_TRY(cudaGetLastError());
     uint8_t* bufs[6] = {g.d_stage[4], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
     uint32_t strides[6] = {256, 32, 96, 0, 0, 4};

@@ -173,7 +173,14 @@ def test_sign_program_against_reference_kats():
     b = vmcompile.compile_program("sign")
     n = len(lines)
     xmd = bytearray(b"".join(O.expand_message_xmd(bytes.fromhex(m), O.DEFAULT_DST, 256) for _, m, _ in lines))
-    sks = bytearray(b"".join((int(sk, 16) % O.R_ORDER).to_bytes(32, "big") for sk, _, _ in lines))
+    z = 0xD201000000010000  # the sign program takes the scalar as four base-|x| digits (api.cu: base_z_digits_kernel)
+
+    def digits(k):
+        a = [(k // z**i) % z for i in range(4)]
+        assert k < z**4
+        return b"".join(a[i].to_bytes(8, "big") for i in (3, 2, 1, 0))
+
+    sks = bytearray(b"".join(digits(int(sk, 16) % O.R_ORDER) for sk, _, _ in lines))
     out, fl = bytearray(96 * n), bytearray(4 * n)
     emu.run_program(b, {0: (xmd, 256), 1: (sks, 32), 2: (out, 96), 5: (fl, 4)}, n)
     flags = struct.unpack("<%di" % n, fl)
