@@ -157,6 +157,7 @@ def verify_section(eng, n, rank, world, dist, torch):
     time verifyBatch of the (world x n)-item batch sharded by index with ONE all-gather of the partial Fp12
     products (config 5; world = 1 is config 3).  Host buffers in, verdict out: this is an end-to-end number."""
     import hashlib
+    import numpy as np
     from noble_bls12_381_b200 import dist as bdist
     from noble_bls12_381_b200 import synth
     dst = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
@@ -210,7 +211,7 @@ def verify_section(eng, n, rank, world, dist, torch):
         rc = eng.lib.bls381_verify_batch_partial(sig_arg, packed, off, pk_cat, n, dst, len(dst), out576, st_buf)
         assert rc == 0, eng.lib.bls381_last_error()
         partial = out576.raw
-        lvl = bdist._level(st_buf[:np_])
+        lvl = bdist._level(np.frombuffer(st_buf, dtype=np.int32, count=np_))
         parts = [partial]
         if world > 1:
             tt = torch.frombuffer(bytearray(partial) + bytearray([lvl, 0, 0, 0]), dtype=torch.uint8).cuda()

@@ -139,7 +139,8 @@ class Engine:
         out = ctypes.create_string_buffer(576)
         st = (ctypes.c_int32 * max(np_, 1))()
         self._check(self.lib.bls381_verify_batch_partial(sig96, packed, off, pks48, n, dst, len(dst), out, st))
-        return out.raw, list(st)[:np_]
+        import numpy as np
+        return out.raw, np.frombuffer(st, dtype=np.int32, count=np_).copy()
 
     def sign_batch(self, sks32: bytes, msgs, dst: bytes) -> bytes:
         n = len(msgs)
