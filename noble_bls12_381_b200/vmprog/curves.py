@@ -164,13 +164,59 @@ class Curve:
         Z3 = F.mul(F.scale(YY, 4), F.scale(YZ, 2))
         return (F.m(X3), F.m(Y3), F.m(Z3))
 
+    # ---- Jacobian doublings for long runs of zero bits of a public scalar ---------------------------------------
+    # (x, y) = (X/Z^2, Y/Z^3).  dbl-2009-l for a = 0: 24 products in 12 micro-ops over Fp2 instead of the 30 / 16 of the
+    # complete homogeneous doubling.  The formulas hold for every point of an odd-order curve, including the point at
+    # infinity in the form (X, Y, 0) with X^3 = Y^2 != 0 (it maps to (X^4, X^6, 0)); additions stay complete (RCB15).
+    def to_jacobian(self, p):
+        F = self.F
+        X, Y, Z = p
+        inf = F.is_zero(Z)
+        ZZ = F.m(F.sqr(Z))
+        one = self._mat_point((F.one(),))[0]
+        return (F.select(inf, one, F.m(F.mul(X, Z))), F.select(inf, one, F.m(F.mul(Y, ZZ))), Z)
+
+    def from_jacobian(self, p):
+        F = self.F
+        X, Y, Z = p
+        ZZ = F.m(F.sqr(Z))
+        return (F.m(F.mul(X, Z)), Y, F.m(F.mul(ZZ, Z)))
+
+    def dbl_jacobian(self, p):
+        F = self.F
+        X, Y, Z = p
+        A = F.m(F.sqr(X))
+        B = F.m(F.sqr(Y))
+        Z3 = F.m(F.mul(F.scale(Y, 2), Z))
+        D = F.m(F.mul(F.scale(X, 4), B))
+        A3 = F.scale(A, 3)
+        X3 = F.m(F.sqr(A3) - F.scale(D, 2))
+        Y3 = F.m(F.mul(A3, D - X3) - F.scale(F.sqr(B), 8))
+        return (X3, Y3, Z3)
+
+    MIN_JACOBIAN_RUN = 4  # shorter runs of doublings do not pay for the two coordinate conversions
+
     def mul_fixed(self, p, k: int):
-        """[k]P for a public constant k (MSB-first double-and-add; complete formulas cover every case)."""
+        """[k]P for a public constant k (MSB-first double-and-add; complete additions cover every case, runs of at least
+        MIN_JACOBIAN_RUN doublings are done in Jacobian coordinates)."""
         acc = p
-        for i in range(k.bit_length() - 2, -1, -1):
-            acc = self.dbl(acc)
-            if (k >> i) & 1:
+        bits = [(k >> i) & 1 for i in range(k.bit_length() - 2, -1, -1)]
+        i = 0
+        while i < len(bits):
+            run = 1  # doublings up to and including the next set bit (or the end)
+            while bits[i + run - 1] == 0 and i + run < len(bits):
+                run += 1
+            if run >= self.MIN_JACOBIAN_RUN:
+                j = self.to_jacobian(acc)
+                for _ in range(run):
+                    j = self.dbl_jacobian(j)
+                acc = self.from_jacobian(j)
+            else:
+                for _ in range(run):
+                    acc = self.dbl(acc)
+            if bits[i + run - 1]:
                 acc = self.add(acc, p)
+            i += run
         return acc
 
     def mul_secret(self, p, nbits: int, bit_fn, window: int = None):

@@ -188,3 +188,67 @@ def test_sign_program_against_reference_kats():
         body = bytearray(out[96 * i : 96 * i + 96])
         body[0] |= 0x80 | (0x40 if flags[i] & 2 else 0) | (0x20 if flags[i] & 1 else 0)
         assert bytes(body).hex() == sig.strip().lower(), i
+
+
+def test_validate_programs_edge_points():
+    """assertValidity (index.ts:383-388 / 633-638) through the fixed-scalar multiplication with Jacobian doubling runs:
+    subgroup points, on-curve points outside the subgroup, a point of the curve's small-order part (a multiple of r of a
+    curve point: its multiples hit the point at infinity in the middle of the ladder) and off-curve points."""
+    r = O.R_ORDER
+    # ---- G1
+    b1 = vmcompile.compile_program("g1_validate")
+    pts, exp = [], []
+    for k in (1, 2, 0xABCDEF):
+        pts.append(O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, k))); exp.append(0)
+    x = 1
+    found = 0
+    while found < 2:
+        x += 1
+        y = O.fp_sqrt((x**3 + 4) % O.P)
+        if y is None:
+            continue
+        p = (x, y, 1)
+        if O.g1_is_torsion_free(p):
+            continue
+        found += 1
+        pts.append((x, y)); exp.append(curves.ST_NOT_IN_SUBGROUP)
+        s = O.pt_multiply_unsafe(O.G1, p, r)  # lands in the cofactor part: small order
+        if not O.pt_is_zero(O.G1, s):
+            pts.append(O.pt_to_affine(O.G1, s)); exp.append(curves.ST_NOT_IN_SUBGROUP)
+        h1 = 0x396C8C005555E1568C00AAAB0000AAAB  # G1 cofactor = 3 * 11^2 * 10177^2 * 859267^2 * 52437899^2
+        for q in (3, 11):  # points of order 3 / 11: the ladder's running multiple IS the point at infinity several times
+            sq = O.pt_multiply_unsafe(O.G1, s, h1 // q)  # s = [r]p (scalars above r are refused by the oracle, as by the reference)
+            if not O.pt_is_zero(O.G1, sq):
+                assert O.pt_is_zero(O.G1, O.pt_multiply_unsafe(O.G1, sq, q))
+                pts.append(O.pt_to_affine(O.G1, sq)); exp.append(curves.ST_NOT_IN_SUBGROUP)
+    pts.append((5, 7)); exp.append(curves.ST_NOT_ON_CURVE)
+    n = len(pts)
+    st = bytearray(4 * n)
+    emu.run_program(b1, {0: (bytearray(b"".join(a.to_bytes(48, "big") + c.to_bytes(48, "big") for a, c in pts)), 96), 5: (st, 4)}, n)
+    assert list(struct.unpack("<%di" % n, st)) == exp
+    # ---- G2
+    b2 = vmcompile.compile_program("g2_validate")
+    pts, exp = [], []
+    for k in (1, 3, 0x123456789):
+        pts.append(O.pt_to_affine(O.G2, O.pt_multiply_unsafe(O.G2, O.G2_BASE, k))); exp.append(0)
+    xx = (1, 1)
+    found = 0
+    while found < 2:
+        xx = (xx[0] + 1, xx[1])
+        y = O.fp2_sqrt(O.fp2_add(O.fp2_pow(xx, 3), O.B2))
+        if y is None:
+            continue
+        p = (xx, y, O.FP2_ONE)
+        if O.g2_is_torsion_free(p):
+            continue
+        found += 1
+        pts.append((xx, y)); exp.append(curves.ST_NOT_IN_SUBGROUP)
+        s = O.pt_multiply_unsafe(O.G2, p, r)
+        if not O.pt_is_zero(O.G2, s):
+            pts.append(O.pt_to_affine(O.G2, s)); exp.append(curves.ST_NOT_IN_SUBGROUP)
+    pts.append(((5, 6), (7, 8))); exp.append(curves.ST_NOT_ON_CURVE)
+    n = len(pts)
+    st = bytearray(4 * n)
+    raw = b"".join(b"".join(v.to_bytes(48, "big") for v in (a[0], a[1], c[0], c[1])) for a, c in pts)
+    emu.run_program(b2, {0: (bytearray(raw), 192), 5: (st, 4)}, n)
+    assert list(struct.unpack("<%di" % n, st)) == exp
