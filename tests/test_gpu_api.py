@@ -35,6 +35,28 @@ def test_sign_all_559_kats(bls, vectors):
     assert bls.sign(vectors[7][1], vectors[7][0].rjust(64, "0")).hex() == vectors[7][2]
 
 
+def test_sign_scalar_digits_edge_cases(bls, vectors):
+    """The sign program takes the scalar as four base-|x| digits (device kernel base_z_digits_kernel): scalars whose
+    digits are all-zero / all-maximal, and unreduced 32-byte scalars k + r, 2^256 - 1 (the C ABI reduces them mod r:
+    [k]H(m) = [k mod r]H(m) on G2) must give the signature of the reduced key."""
+    from noble_bls12_381_b200 import _lib
+    eng = _lib.engine()
+    dst = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
+    r = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    z = 0xD201000000010000
+    keys = [1, z - 1, z, z * z, z**3 + 1, (z - 1) * (1 + z + z * z), r - 1, int(vectors[3][0], 16) % r]
+    msgs = [bytes.fromhex(vectors[3][1])] * len(keys)
+    base = eng.sign_batch(b"".join(k.to_bytes(32, "big") for k in keys), msgs, dst)
+    from oracle import noble_oracle as O
+    for i, k in enumerate(keys):  # against the CPU restatement of index.ts:746-752
+        assert base[96 * i: 96 * i + 96] == O.sign(msgs[i], k), i
+    assert base[96 * 7: 96 * 8].hex() == vectors[3][2]
+    unreduced = [(k + r) for k in keys if k + r < 1 << 256] + [(1 << 256) - 1]
+    got = eng.sign_batch(b"".join(k.to_bytes(32, "big") for k in unreduced), msgs[: len(unreduced)], dst)
+    want = eng.sign_batch(b"".join((k % r).to_bytes(32, "big") for k in unreduced), msgs[: len(unreduced)], dst)
+    assert got == want
+
+
 def test_get_public_key_and_verify(bls, vectors):
     """index.test.ts:308-336"""
     for i in range(4):
