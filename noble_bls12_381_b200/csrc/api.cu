@@ -81,8 +81,8 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6]; p.staged_mask = h[7];
     const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
-    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
-    if (p.nrec == 0 || p.nrec > 32767) return fail(BLS381_EPROGRAM, "record count out of range (15-bit progress counters): " + name);
+    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10 && p.warps != 12) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    if (p.nrec == 0 || p.nrec > (p.warps <= 8 ? 32767u : (p.warps <= 10 ? 4095u : 1023u))) return fail(BLS381_EPROGRAM, "record count out of range for the progress-requirement fields: " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
@@ -220,6 +220,7 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     if (p->warps == 6) rc = ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
     if (p->warps == 8) rc = launch_w<8, 2>(L, grid, smem, s);
     if (p->warps == 10) rc = launch_w<10, 2>(L, grid, smem, s);
+    if (p->warps == 12) rc = launch_w<12, 2>(L, grid, smem, s);
     if (d_trace) {
         cudaStreamSynchronize(s);
         std::vector<uint32_t> h((size_t)trace_ctas * p->warps * p->nrec * 8);

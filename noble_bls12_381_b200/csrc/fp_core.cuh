@@ -25,12 +25,27 @@
 namespace fpc {
 
 FPC_DEV void acc_zero(Acc& A) {
+#if BLS381_MAC24
+#pragma unroll
+    for (int i = 0; i < 25; ++i) A.a[i] = 0;
+    return;
+#else
 #pragma unroll
     for (int i = 0; i < 12; ++i) A.e[i] = 0;
 #pragma unroll
     for (int i = 0; i < 11; ++i) A.o[i] = 0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) A.c[i] = 0;
+#endif
+}
+
+// always 0, but data-dependent on the accumulator (keeps a clock read behind the multiply-accumulate in tracing builds)
+FPC_DEV uint32_t acc_dep(const Acc& A) {
+#if BLS381_MAC24
+    return A.a[23] & 0u;
+#else
+    return (uint32_t)(A.e[11] & 0u);
+#endif
 }
 
 FPC_DEV void copy12(uint32_t* r, const uint32_t* a) {

@@ -381,7 +381,7 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W, uin
             load_operand_pair(x, y, c, wx, wy, xmask);
             if (TRACE) { k1 = phase_clock() + (x[0] & y[0] & 0u); ph[0] += k1 - k0; }
             fpc::acc_mac(A, x, y);
-            if (TRACE) ph[1] += phase_clock() + (uint32_t)(A.e[11] & 0u) - k1;
+            if (TRACE) ph[1] += phase_clock() + fpc::acc_dep(A) - k1;
         }
         uint32_t k2 = 0;
         if (TRACE) k2 = phase_clock();

@@ -173,17 +173,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vm_kernel(const Launch L) {
                     wait_progress(progress, 2, q1 & 0xFFFF, L.pad); wait_progress(progress, 3, q1 >> 16, L.pad);
                     wait_progress(progress, 4, q2 & 0xFFFF, L.pad); wait_progress(progress, 5, q2 >> 16, L.pad);
                     wait_progress(progress, 6, q3 & 0xFFFF, L.pad); wait_progress(progress, 7, q3 >> 16, L.pad);
-                } else {           // ten 12-bit fields packed little-endian over the four words
+                } else {           // WARPS fields of 12 bits (up to 10 warps) or 10 bits (12 warps), little-endian over the four words
                     const uint32_t q0 = __shfl_sync(0xffffffffu, cur, 27), q1 = __shfl_sync(0xffffffffu, cur, 29);
                     const uint32_t q2 = __shfl_sync(0xffffffffu, cur, 30), q3 = __shfl_sync(0xffffffffu, cur, 31);
                     const uint64_t lo = ((uint64_t)q1 << 32) | q0, hi = ((uint64_t)q3 << 32) | q2;
+                    constexpr int FW = WARPS <= 10 ? 12 : 10;
+                    constexpr uint32_t FM = (1u << FW) - 1u;
 #pragma unroll
-                    for (int k = 0; k < WARPS && k < 10; ++k) {
-                        const int bit = 12 * k;
+                    for (int k = 0; k < WARPS; ++k) {
+                        const int bit = FW * k;
                         uint32_t need;
-                        if (bit + 12 <= 64) need = (uint32_t)(lo >> bit) & 0xFFF;
-                        else if (bit >= 64) need = (uint32_t)(hi >> (bit - 64)) & 0xFFF;
-                        else need = (uint32_t)((lo >> bit) | (hi << (64 - bit))) & 0xFFF;
+                        if (bit + FW <= 64) need = (uint32_t)(lo >> bit) & FM;
+                        else if (bit >= 64) need = (uint32_t)(hi >> (bit - 64)) & FM;
+                        else need = (uint32_t)((lo >> bit) | (hi << (64 - bit))) & FM;
                         wait_progress(progress, k, need, L.pad);
                     }
                 }
@@ -240,5 +242,6 @@ template __global__ void vm_kernel<6, 2>(const Launch);
 template __global__ void vm_kernel<6, 3>(const Launch);
 template __global__ void vm_kernel<8, 2>(const Launch);
 template __global__ void vm_kernel<10, 2>(const Launch);
+template __global__ void vm_kernel<12, 2>(const Launch);
 
 }  // namespace vm

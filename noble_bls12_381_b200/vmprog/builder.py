@@ -837,7 +837,7 @@ class Builder:
         """Returns (prog: bytes [W][nrec][32 words], nrec).  Words 27, 29, 30, 31 hold eight 16-bit progress
         requirements (warps 0..7)."""
         W = self.warps
-        assert W <= 10
+        assert W <= 12
         streams = []
         for w in range(W):
             recs = []
@@ -890,11 +890,12 @@ class Builder:
                     words[29] = wt[2] | (wt[3] << 16)
                     words[30] = wt[4] | (wt[5] << 16)
                     words[31] = wt[6] | (wt[7] << 16)
-                else:  # ten 12-bit fields, little-endian over words 27, 29, 30, 31
-                    assert max(wt) < 4096
+                else:  # W fields of 12 bits (W <= 10) or 10 bits (W = 12), little-endian over words 27, 29, 30, 31
+                    fw = 12 if W <= 10 else 10
+                    assert max(wt) < (1 << fw)
                     big = 0
                     for k, v_ in enumerate(wt):
-                        big |= v_ << (12 * k)
+                        big |= v_ << (fw * k)
                     words[27], words[29], words[30], words[31] = [(big >> (32 * j)) & 0xFFFFFFFF for j in range(4)]
                 recs.append(words)
             streams.append(recs)

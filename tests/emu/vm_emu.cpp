@@ -52,8 +52,11 @@ int vm_emu_run(const uint32_t* prog, int warps, int nrec, const uint32_t* consts
                 bool ok = true;
                 if (rec[0] & vm::H_BAR) {
                     const uint32_t ww[4] = {rec[27], rec[29], rec[30], rec[31]};
-                    for (int k = 0; k < 8 && k < warps; ++k) {
-                        uint32_t need = (ww[k / 2] >> (16 * (k & 1))) & 0xFFFF;
+                    const int fw = warps <= 8 ? 16 : (warps <= 10 ? 12 : 10);  // field width, as in vm_kernel.cu
+                    const unsigned __int128 big = ((unsigned __int128)ww[3] << 96) | ((unsigned __int128)ww[2] << 64) |
+                                                  ((unsigned __int128)ww[1] << 32) | ww[0];
+                    for (int k = 0; k < warps; ++k) {
+                        uint32_t need = (uint32_t)(big >> (fw * k)) & ((1u << fw) - 1u);
                         if (pc[k] < need) ok = false;
                     }
                 }
