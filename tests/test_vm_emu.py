@@ -159,6 +159,20 @@ def test_pairs_per_lane_miller_product_on_emulator(k):
     assert bytes(part[576:]) == O.fp12_to_bytes(prod(mill[32 * k :]))
 
 
+@pytest.mark.parametrize("warps", [10, 12])
+def test_wide_cta_requirement_fields_on_emulator(warps, golden_dir):
+    """10- and 12-warp CTAs pack their progress requirements as 12- / 10-bit fields (vm_kernel.cu, builder.encode): the
+    final-exponentiation KAT (pairing.test.ts:65-96) through programs scheduled for those widths."""
+    import json
+    b = vmcompile.compile_program("final_exp", warps=warps)
+    b.check_hazards()
+    k = json.load(open(os.path.join(golden_dir, "pairing_kats.json")))
+    fin = O.fp12_from_twelve([int(x, 16) for x in k["final_exp_in"]])
+    out = bytearray(576)
+    emu.run_program(b, {2: (out, 576), 3: (bytearray(O.fp12_to_bytes(fin)), 576)}, 1)
+    assert [int.from_bytes(out[48 * i : 48 * i + 48], "big") for i in range(12)] == [int(x, 16) for x in k["final_exp_out"]]
+
+
 def test_synth_matches_oracle_multiples():
     g1, g2 = synth.multiples_wire(5)
     for i in range(5):
