@@ -108,7 +108,8 @@ int bls381_verify_batch_partial(const uint8_t* sig96_or_null, const uint8_t* msg
 /* sign(message, privateKey) for byte messages                                   replaces index.ts:746-752
  * (hashToCurve + constant-time scalar multiplication math.ts:1061-1078 + toSignature index.ts:586-598).
  *   sks32: n x 32 B big-endian scalars already normalised to 0 < sk < r (normalizePrivKey index.ts:269-279 is
- *   host-side argument checking); out_sig96: n x 96 B compressed signatures.                               */
+ *   host-side argument checking; larger 32-byte values are reduced mod r on the device, sk = 0 yields the encoding
+ *   of the point at infinity); out_sig96: n x 96 B compressed signatures.                                   */
 int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
                       const uint8_t* dst, size_t dst_len, uint8_t* out_sig96);
 /* aggregatePublicKeys(Hex[]) / aggregateSignatures(Hex[])                       replaces index.ts:773-788
