@@ -129,7 +129,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(cores * 160, 1024)
+    per_step = max(cores * 1600, 4096)  # ~3 s of all-core CPU work per pass, two passes per step
     for _ in range(args.warmup and 1):
         cpu_baseline(cores)
     vals = []
@@ -401,7 +401,7 @@ def main():
         if vb is not None:
             line["verify_batch"] = vb
         if not args.no_cpu_baseline:
-            v, cores, cnt = cpu_baseline(max((os.cpu_count() or 1) * 160, 1024))
+            v, cores, cnt = cpu_baseline(max((os.cpu_count() or 1) * 1600, 4096))  # ~10 s of all-core CPU work in total
             line["cpu_baseline"] = {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port",
                                     "sample": f"{cnt} pairings of the same workload ({cnt // cores} per core), plain-C port of math.ts/index.ts (oracle/c, reference's Karatsuba tower formulas), one thread per core, outputs checked against the reference fixtures; the TypeScript original is ~43 pairings/s/core by its own comment (index.ts:719)"}
         print(json.dumps(line))
