@@ -14,7 +14,8 @@
 // evaluation math.ts:1331-1388) with LAZY REDUCTION: one Montgomery reduction per output coefficient
 // instead of one per Fp product.  The per-warp instruction streams ("programs") are produced by the
 // host-side builder (noble_bls12_381_b200/vmprog) which also schedules independent micro-ops across
-// the warps of a CTA and allocates slots; barriers (`bar.sync`) separate dependent steps.
+// the warps of a CTA and allocates slots; dependent micro-ops are ordered by per-warp progress counters that a record
+// names in its requirement words (static dataflow schedule, no `bar.sync` inside a batch).
 //
 // This header is shared by the CUDA kernel (vm_kernel.cu) and the CPU emulation used by the tests
 // (tests/emu/vm_emu.cpp) -- the emulation exists to validate programs without a GPU and is not part
@@ -50,7 +51,8 @@ static constexpr int kConstSlots = 64;
 //     word B: [7:0] yA  [15:8] yB  [19:16] cA                [23:20] cB  [31:24] yflags
 // words 26, 28   : E epilogue operands (same 1-word operand encoding)
 // words 27,29,30,31: eight 16-bit progress requirements (warp 0..7): this record may start only when
-//                  warp w has completed at least that many records of its stream (0 = no requirement)
+//                  warp w has completed at least that many records of its stream (0 = no requirement); CTAs of 10 / 12
+//                  warps pack ten 12-bit / twelve 10-bit fields into the same four words
 // operand flags  : bit0 CONST  (A/B index the constant table instead of slots)
 //                  bit1 GLOBAL (A = buffer id, B = byte offset/16 of a big-endian field; cA = number of top
 //                       bits to clear (compression flags), cB = 0: 48-byte field, 1: 32-byte field)
