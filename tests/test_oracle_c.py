@@ -37,3 +37,68 @@ def test_c_oracle_miller_matches_python_oracle():
         g2 = b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
         f = O.miller_loop(O.calc_pairing_precomputes(*q), p)
         assert C.pairing_batch(g1, g2, 1, False) == O.fp12_to_bytes(f)
+
+
+# ---- oracle/c/bls381_curves.c: sign / hash-to-curve / key path ------------------------------------------------
+def _sign_kats():
+    return [l.split(":") for l in open(os.path.join(GOLDEN, "sign_g2_vectors.txt")).read().split("\n") if l]
+
+
+def test_c_oracle_sign_all_559_reference_kats():
+    # test/bls12-381-g2-test-vectors.txt (index.test.ts:287-293): priv:msg:sig
+    kats = _sign_kats()
+    assert len(kats) == 559
+    sks = b"".join(int(k, 16).to_bytes(32, "big") for k, _, _ in kats)
+    sigs = C.sign_batch(sks, [bytes.fromhex(m) for _, m, _ in kats], O.DEFAULT_DST)
+    for i, (_, _, sig) in enumerate(kats):
+        assert sigs[96 * i: 96 * i + 96].hex() == sig.strip().lower(), i
+
+
+def test_c_oracle_hash_to_curve_g2_reference_vectors():
+    # test/hashToCurve.test.ts: kilic `..._TESTGEN` and RFC `QUUX-V01-CS02-...` random-oracle suites (G2 uncompressed:
+    # x.c1 || x.c0 || y.c1 || y.c0)
+    d = json.load(open(os.path.join(GOLDEN, "hash_to_curve.json")))
+    for key in ("g2_kilic_ro", "g2_rfc_ro"):
+        dst = d[key]["dst"].encode("latin1")
+        msgs = [v["msg"].encode("latin1") for v in d[key]["vectors"]]
+        out = C.hash_to_g2_batch(msgs, dst)
+        for i, v in enumerate(d[key]["vectors"]):
+            a = out[192 * i: 192 * i + 192]
+            wire = a[48:96] + a[0:48] + a[144:192] + a[96:144]
+            assert wire.hex() == v["expected"], (key, i)
+    # long DST (> 255 bytes is hashed first, index.ts:214) and long messages against the Python oracle
+    long_dst = b"Q" * 300
+    for m in (b"", b"x" * 200, bytes(range(256)) * 3):
+        (x, y) = O.pt_to_affine(O.G2, O.g2_hash_to_curve(m, long_dst))
+        assert C.hash_to_g2_batch([m], long_dst) == b"".join(v.to_bytes(48, "big") for v in (x[0], x[1], y[0], y[1]))
+
+
+def test_c_oracle_public_keys_match_zkcrypto_g1_vectors():
+    # test/zkcrypto/g1_compressed_valid_test_vectors.dat: entry i = compressed i * G1 (deterministic.test.ts:49-64)
+    g1c = open(os.path.join(GOLDEN, "zkcrypto_g1_compressed.dat"), "rb").read()
+    n = 1000
+    pks = C.get_public_key_batch(b"".join(i.to_bytes(32, "big") for i in range(1, n)))
+    assert pks == g1c[48: 48 * n]
+    # unreduced scalars are taken mod r (normalizePrivKey, index.ts:269-279)
+    k = O.R_ORDER + 5
+    assert C.get_public_key_batch(k.to_bytes(32, "big")) == g1c[48 * 5: 48 * 6]
+
+
+def test_c_oracle_scalar_multiples_of_the_generators():
+    g1u = open(os.path.join(GOLDEN, "zkcrypto_g1_uncompressed.dat"), "rb").read()
+    g2u = open(os.path.join(GOLDEN, "zkcrypto_g2_uncompressed.dat"), "rb").read()
+    ks = list(range(1, 200))
+    a = b"".join(k.to_bytes(32, "big") for k in ks)
+    g1, g2 = C.scalar_mul_bases_batch(a, a)
+    for j, k in enumerate(ks):
+        assert g1[96 * j: 96 * j + 96] == g1u[96 * k: 96 * k + 96]
+        q = g2[192 * j: 192 * j + 192]  # wire order x.c0 x.c1 y.c0 y.c1 ; zkcrypto order x.c1 x.c0 y.c1 y.c0
+        assert q[48:96] + q[0:48] + q[144:192] + q[96:144] == g2u[192 * k: 192 * k + 192]
+    rng = random.Random(11)
+    for _ in range(3):
+        ka, kb = rng.randrange(1, O.R_ORDER), rng.randrange(1, O.R_ORDER)
+        g1, g2 = C.scalar_mul_bases_batch(ka.to_bytes(32, "big"), kb.to_bytes(32, "big"))
+        p = O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, ka))
+        q = O.pt_to_affine(O.G2, O.pt_multiply_unsafe(O.G2, O.G2_BASE, kb))
+        assert g1 == p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+        assert g2 == b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
