@@ -28,19 +28,30 @@ BYTES_PER_PAIRING = 288 + 576  # algorithmic HBM bytes
 
 
 def issued_imad_per_item(program_path, wide_per_product=144):
-    """IMAD.WIDE the interpreter executes per item for a tower-VM program image: products x 144 (or 108 with the
-    Karatsuba core) + Montgomery reductions x 156, counted from the record headers (opcode 1 = MAC, T = bits 16..19)."""
+    """IMAD.WIDE the interpreter executes per item for a tower-VM program image: products x 144 + Montgomery reductions
+    x 156, counted from the records (256 bytes each).  One-output records: opcode 1, T = bits 16..19 of word 0.
+    Two-output records: opcode 5, entries per group in word 1 (4 x 5 bits; a fused entry pair is ONE product and shows as
+    two entries whose first x word has flag bit 31), one reduction per result (one for the H_SINGLE form, bit 24)."""
     import struct
     raw = open(program_path, "rb").read()
     _magic, _ver, warps, nrec, nconst, _ns, _nf, _st = struct.unpack_from("<8I", raw, 0)
     base = 32 + nconst * 48
     products = reductions = 0
     for k in range(warps * nrec):
-        hdr = struct.unpack_from("<I", raw, base + k * 128)[0]
-        if hdr & 0xFF == 1:
-            t = (hdr >> 16) & 0xF
+        w = struct.unpack_from("<64I", raw, base + k * 256)
+        op = w[0] & 0xFF
+        if op == 1:
+            t = (w[0] >> 16) & 0xF
             products += t
             reductions += 1 if t else 0
+        elif op == 5:
+            n = [(w[1] >> (5 * g)) & 31 for g in range(4)]
+            ent = sum(n)
+            fused = sum(1 for e in range(ent) if w[4 + 2 * e] >> 31)
+            products += ent - fused
+            single = (w[0] >> 24) & 1
+            shared = (n[0] + n[1]) > 0
+            reductions += 1 if single else (2 if shared else (1 if n[2] else 0) + (1 if n[3] else 0))
     return products * wide_per_product + reductions * 156, products, reductions
 
 

@@ -21,6 +21,7 @@ namespace {
 
 struct Program {
     uint32_t warps = 0, nrec = 0, nconst = 0, nslots = 0, nfar = 0, staged_mask = 0;
+    bool mac2 = false;  // two-output record format (header word 7, bit 31)
     uint32_t* d_prog = nullptr;
     uint32_t* d_consts = nullptr;
 };
@@ -76,13 +77,13 @@ int load_image(const std::string& name, const uint8_t* img, size_t len) {
     if (len < 32) return fail(BLS381_EPROGRAM, "program image too short: " + name);
     uint32_t h[8];
     memcpy(h, img, 32);
-    if (h[0] != kMagic || h[1] != 1) return fail(BLS381_EPROGRAM, "bad program magic/version: " + name);
+    if (h[0] != kMagic || h[1] != 2) return fail(BLS381_EPROGRAM, "bad program magic/version: " + name);
     Program p;
-    p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6]; p.staged_mask = h[7];
-    const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * 128;
+    p.warps = h[2]; p.nrec = h[3]; p.nconst = h[4]; p.nslots = h[5]; p.nfar = h[6]; p.staged_mask = h[7] & 0xFFu; p.mac2 = (h[7] >> 31) != 0;
+    const size_t cbytes = (size_t)p.nconst * 48, pbytes = (size_t)p.warps * p.nrec * vm::kRecWords * 4;
     if (len != 32 + cbytes + pbytes) return fail(BLS381_EPROGRAM, "program image size mismatch: " + name);
-    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8 && p.warps != 10 && p.warps != 12) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
-    if (p.nrec == 0 || p.nrec > (p.warps <= 8 ? 32767u : (p.warps <= 10 ? 4095u : 1023u))) return fail(BLS381_EPROGRAM, "record count out of range for the progress-requirement fields: " + name);
+    if (p.warps != 2 && p.warps != 4 && p.warps != 6 && p.warps != 8) return fail(BLS381_EPROGRAM, "unsupported warp count: " + name);
+    if (p.nrec == 0 || p.nrec > 32767u) return fail(BLS381_EPROGRAM, "record count out of range for the progress-requirement fields: " + name);
     CUDA_TRY(cudaMalloc(&p.d_consts, std::max<size_t>(cbytes, 48)));
     CUDA_TRY(cudaMalloc(&p.d_prog, pbytes));
     CUDA_TRY(cudaMemcpy(p.d_consts, img + 32, cbytes, cudaMemcpyHostToDevice));
@@ -123,12 +124,17 @@ int get_program(const char* name, Program** out) {
     return BLS381_OK;
 }
 
-template <int W, int MINB>
-int launch_w(const vm::Launch& L, int grid, size_t smem, cudaStream_t s) {
-    CUDA_TRY(cudaFuncSetAttribute(vm::vm_kernel<W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vm::vm_kernel<W, MINB><<<grid, W * 32, smem, s>>>(L);
+template <int W, int MINB, int MODE>
+int launch_m(const vm::Launch& L, int grid, size_t smem, cudaStream_t s) {
+    CUDA_TRY(cudaFuncSetAttribute(vm::vm_kernel<W, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vm::vm_kernel<W, MINB, MODE><<<grid, W * 32, smem, s>>>(L);
     CUDA_TRY(cudaGetLastError());
     return BLS381_OK;
+}
+
+template <int W, int MINB>
+int launch_w(const vm::Launch& L, bool mac2, int grid, size_t smem, cudaStream_t s) {
+    return mac2 ? launch_m<W, MINB, vm::MODE_MAC2>(L, grid, smem, s) : launch_m<W, MINB, vm::MODE_LEGACY>(L, grid, smem, s);
 }
 
 int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int nbuf, size_t n, cudaStream_t s) {
@@ -215,12 +221,10 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
     }
     g.launches.fetch_add(1);
     rc = BLS381_EPROGRAM;
-    if (p->warps == 2) rc = launch_w<2, 8>(L, grid, smem, s);
-    if (p->warps == 4) rc = launch_w<4, 4>(L, grid, smem, s);
-    if (p->warps == 6) rc = ctas_per_sm >= 3 ? launch_w<6, 3>(L, grid, smem, s) : launch_w<6, 2>(L, grid, smem, s);
-    if (p->warps == 8) rc = launch_w<8, 2>(L, grid, smem, s);
-    if (p->warps == 10) rc = launch_w<10, 2>(L, grid, smem, s);
-    if (p->warps == 12) rc = launch_w<12, 2>(L, grid, smem, s);
+    if (p->warps == 2) rc = launch_w<2, 8>(L, p->mac2, grid, smem, s);
+    if (p->warps == 4) rc = launch_w<4, 4>(L, p->mac2, grid, smem, s);
+    if (p->warps == 6) rc = launch_w<6, 3>(L, p->mac2, grid, smem, s);
+    if (p->warps == 8) rc = launch_w<8, 2>(L, p->mac2, grid, smem, s);
     if (d_trace) {
         cudaStreamSynchronize(s);
         std::vector<uint32_t> h((size_t)trace_ctas * p->warps * p->nrec * 8);

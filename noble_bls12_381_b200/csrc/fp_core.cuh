@@ -5,6 +5,8 @@
 //   * acc_mac   : 768-bit accumulator += a*b       (144 IMAD.WIDE.U32[.X], no reduction)
 //   * acc_redc  : Montgomery reduction of the accumulator (12 x (1 IMAD + 12 IMAD.WIDE.U32.X))
 //   * add12/sub12/csub_kp: carry-chain add/sub and conditional subtraction of k*p (immediates)
+//   * acc_collapse / acc_from_wide / add24 / sub24 / kKP2: unreduced 768-bit sums of products as plain 24-word values,
+//     shared between the two outputs of a two-output record (Karatsuba over Fp2 without an extra reduction, vm.cuh)
 // "Lazy reduction": tower formulas accumulate many products into one accumulator and reduce once.
 //
 // The generated primitives also have a portable C++ body (`#else` of __CUDA_ARCH__) used ONLY by the CPU
@@ -25,27 +27,17 @@
 namespace fpc {
 
 FPC_DEV void acc_zero(Acc& A) {
-#if BLS381_MAC24
-#pragma unroll
-    for (int i = 0; i < 25; ++i) A.a[i] = 0;
-    return;
-#else
 #pragma unroll
     for (int i = 0; i < 12; ++i) A.e[i] = 0;
 #pragma unroll
     for (int i = 0; i < 11; ++i) A.o[i] = 0;
 #pragma unroll
-    for (int i = 0; i < 13; ++i) A.c[i] = 0;
-#endif
+    for (int i = 0; i < 12; ++i) A.c[i] = 0;
 }
 
 // always 0, but data-dependent on the accumulator (keeps a clock read behind the multiply-accumulate in tracing builds)
 FPC_DEV uint32_t acc_dep(const Acc& A) {
-#if BLS381_MAC24
-    return A.a[23] & 0u;
-#else
     return (uint32_t)(A.e[11] & 0u);
-#endif
 }
 
 FPC_DEV void copy12(uint32_t* r, const uint32_t* a) {

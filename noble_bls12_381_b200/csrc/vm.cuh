@@ -27,8 +27,10 @@
 
 namespace vm {
 
-static constexpr int kRecWords = 32;       // one micro-op record = 128 bytes
+static constexpr int kRecWords = 64;       // one micro-op record = 256 bytes
+static constexpr int kWaitWord = 60;       // words 60..63: progress requirements
 static constexpr int kMaxTerms = 12;
+static constexpr int kMaxEntries2 = 24;    // product entries of a two-output record (words 4..51)
 static constexpr int kMaxEpi = 2;
 static constexpr int kSlotWords = 12 * 32; // 1536 B per slot
 static constexpr int kMaxBuffers = 8;
@@ -50,17 +52,37 @@ static constexpr int kConstSlots = 64;
 //     word A: [7:0] xA  [15:8] xB  [19:16] cA (signed 4-bit)  [23:20] cB  [31:24] xflags
 //     word B: [7:0] yA  [15:8] yB  [19:16] cA                [23:20] cB  [31:24] yflags
 // words 26, 28   : E epilogue operands (same 1-word operand encoding)
-// words 27,29,30,31: eight 16-bit progress requirements (warp 0..7): this record may start only when
+// words 60..63   : eight 16-bit progress requirements (warp 0..7): this record may start only when
 //                  warp w has completed at least that many records of its stream (0 = no requirement); CTAs of 10 / 12
 //                  warps pack ten 12-bit / twelve 10-bit fields into the same four words
+//
+// opcode OP_MAC2 : TWO outputs that share products (an Fp2 coefficient pair):
+//                      dst0 = ps0 * MontRed( S_P + S_M + S_0 ) + epilogue0
+//                      dst1 = ps1 * MontRed( S_P - S_M + S_1 ) + epilogue1
+//                  with four groups of product entries: S_M (counted +1 in dst0, -1 in dst1), S_P (+1 in both), S_0, S_1.
+//                  S_M and S_P are kept UNREDUCED (768-bit sums of products, 24 words per lane) and are shared by the two
+//                  accumulations, so an Fp2 product costs three Fp products (Karatsuba: x0*y0 in S_M, (-x1)*y1 in S_P,
+//                  (x0+x1)*(y0+y1) in S_1) and still only one Montgomery reduction per output coefficient (the
+//                  reference reduces every product, math.ts:451-462).  The 24-word intermediate lives in the record's own
+//                  two destination slots until the first result is stored; no extra shared memory.
+//     word 0: [7:0] opcode  [15:8] dst0  [23:16] dst1  [25] has_waits
+//     word 1: [4:0] nM  [9:5] nP  [14:10] n0  [19:15] n1 (entries per group)  [21:20] E0  [23:22] E1  [26:24] ncorr0  [29:27] ncorr1
+//     word 0 (cont.): [24] H_SINGLE: one result only (group 0 -> dst0) with the flag bits 26..31 of the one-output format
+//     word 2: [6:0] K: S_P - S_M + K*p^2 >= 0 (K >= bound of S_M in units of p^2)  [10:8] ps0  [14:12] ps1
+//     word 3: H_SINGLE records: [7:0] dst buffer id  [15:8] dst field  [31:24] padding constant
+//     words 4..51 : product entries, 2 operand words each, in the order M, P, 0, 1.  An entry whose x word has flag bit 7
+//                   (F_FUSE) is ADDED operand-wise to the next entry before the product: x = x_a + x_b, y = y_a + y_b
+//                   (an operand word 0 in the second entry = nothing to add): operands of up to four slots
+//     words 52,53 : epilogue operands of dst0;  words 54,55 : epilogue operands of dst1
 // operand flags  : bit0 CONST  (A/B index the constant table instead of slots)
 //                  bit1 GLOBAL (A = buffer id, B = byte offset/16 of a big-endian field; cA = number of top
 //                       bits to clear (compression flags), cB = 0: 48-byte field, 1: 32-byte field)
 //                  bit2 XLANE  (read the slot column of lane ^ mask)
 //                  bit3 SIMPLE (operand is exactly one shared-memory slot, coefficient +1: fast path)
 //                  bits 4..6: pre-decoded fast mode for shared-memory slots: 1 = -A, 2 = A+B, 3 = A-B, 4 = -A-B, 5 = 2A
-enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3, OP_INV = 4 };
-enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8 };
+enum : uint32_t { OP_NOP = 0, OP_MAC = 1, OP_SEL = 2, OP_BIT = 3, OP_INV = 4, OP_MAC2 = 5 };
+enum : uint32_t { F_CONST = 1, F_GLOBAL = 2, F_XLANE = 4, F_SIMPLE = 8, F_FUSE = 0x80 };
+static constexpr uint32_t H_SINGLE = 1u << 24;  // OP_MAC2 only: one result (group 0, dst0); word 3 = destination / padding info
 static constexpr uint32_t H_BAR = 1u << 25;
 static constexpr uint32_t H_DSTG = 1u << 26;
 static constexpr uint32_t H_DSTBATCH = 1u << 28;  // global store by lane 0 only, at index item/32
@@ -98,24 +120,48 @@ struct Launch {
 };
 static constexpr uint32_t kNoStage = 0xFFFFFFFFu;
 
-// ---- per-lane execution context -------------------------------------------------------------------
-struct Ctx {
-    uint32_t* slots;         // shared memory slots
-    const uint32_t* consts;  // constant table (shared memory copy on device)
+// ---- execution context ------------------------------------------------------------------------------------
+// Cold: what a record needs only occasionally (far slots, wire-format buffers, padding).  On the device it is ONE struct in
+// shared memory per CTA, addressed directly: keeping these ~20 values in registers of every thread is what pushed the
+// interpreter loop over its 128-register budget once the two-output records were added.
+struct Cold {
+    uint32_t nslots;         // shared-memory slots (slot numbers >= nslots are far slots)
+    uint32_t pad0;
     uint32_t* far;           // this CTA's far slots
-    uint32_t nslots;
-    uint32_t lane;
-    uint32_t item;           // global item index of this lane (clamped to n_items-1 for loads)
+    const uint32_t* consts;  // constant table (generic pointer; the hot path uses Ctx::cbase)
+    const uint8_t* stage;    // shared-memory staging area filled by TMA (nullptr: read inputs from global memory)
+    uint32_t n_items;
     uint32_t batch;          // index of the 32-item batch being processed
-    bool store_ok;           // lane < n_items
-    const Buffer* buf;
-    const uint8_t* stage;    // shared-memory staging area filled by TMA (nullptr in the CPU emulation)
-    const uint32_t* stage_off;
-    // device only: 32-bit shared-window addresses, computed ONCE per thread (the generic-pointer path re-derives the
+    Buffer buf[kMaxBuffers];
+    uint32_t stage_off[kMaxBuffers];
+};
+struct Ctx {
+    // device: 32-bit shared-window addresses, computed ONCE per thread (the generic-pointer path re-derives the
     // shared window base with S2UR/ULEA and re-reads SR_TID before every access, ~5 % of the warp time in the v7 profile)
     uint32_t sbase;          // &slots[0] + lane * 16
     uint32_t cbase;          // &consts[0]
+    // CPU emulation only (on the device the lane is threadIdx.x & 31 and everything else is in `g_cold`)
+    uint32_t lane;
+    uint32_t* slots;
+    const Cold* cold;
 };
+#if defined(__CUDACC__)
+__shared__ Cold g_cold;
+#endif
+#if defined(__CUDA_ARCH__)
+#define VM_COLD(c) g_cold
+#define VM_LANE(c) (threadIdx.x & 31u)
+#else
+#define VM_COLD(c) (*(c).cold)
+#define VM_LANE(c) ((c).lane)
+#endif
+#define VM_NSLOTS(c) (VM_COLD(c).nslots)
+// lane's item: index in the batch arrays (clamped to n_items - 1 for loads); store_ok: the lane is not padding
+FPC_DEV bool ctx_store_ok(const Ctx& c) { return VM_COLD(c).batch * 32u + VM_LANE(c) < VM_COLD(c).n_items; }
+FPC_DEV uint32_t ctx_item(const Ctx& c) {
+    const uint32_t item = VM_COLD(c).batch * 32u + VM_LANE(c), last = VM_COLD(c).n_items - 1u;
+    return item < last ? item : last;
+}
 
 #if !defined(BLS381_CACHED_SMEM)
 #define BLS381_CACHED_SMEM 1
@@ -136,10 +182,10 @@ FPC_DEV void sts128(uint32_t addr, const uint32_t* r) {
 
 // start of this lane's record in input buffer `bufid` (TMA-staged copy in shared memory when available)
 FPC_DEV const uint8_t* wire_record(const Ctx& c, uint32_t bufid) {
-    const Buffer& b = c.buf[bufid];
-    if (c.stage != nullptr && c.stage_off[bufid] != kNoStage && c.store_ok)
-        return c.stage + c.stage_off[bufid] + (size_t)c.lane * b.stride;
-    return b.base + (size_t)c.item * b.stride;
+    const Buffer& b = VM_COLD(c).buf[bufid];
+    if (VM_COLD(c).stage != nullptr && VM_COLD(c).stage_off[bufid] != kNoStage && ctx_store_ok(c))
+        return VM_COLD(c).stage + VM_COLD(c).stage_off[bufid] + (size_t)VM_LANE(c) * b.stride;
+    return b.base + (size_t)ctx_item(c) * b.stride;
 }
 
 FPC_DEV uint32_t bswap32(uint32_t v) {
@@ -176,30 +222,30 @@ FPC_DEV void store_col(uint32_t* s, const uint32_t* r) {
 }
 
 FPC_DEV void load_slot(uint32_t* r, const Ctx& c, uint32_t slot, uint32_t lane) {
-    if (slot < c.nslots) {
+    if (slot < VM_NSLOTS(c)) {
 #if VM_SMEM_ASM
-        const uint32_t a = c.sbase + slot * (kSlotWords * 4u) + (lane - c.lane) * 16u;
+        const uint32_t a = c.sbase + slot * (kSlotWords * 4u) + (lane - VM_LANE(c)) * 16u;
 #pragma unroll
         for (int q = 0; q < 3; ++q) lds128(r + 4 * q, a + q * 512u);
 #else
         load_col(r, c.slots + slot * kSlotWords + lane * 4);
 #endif
     } else {
-        load_col(r, c.far + (slot - c.nslots) * kSlotWords + lane * 4);
+        load_col(r, VM_COLD(c).far + (slot - VM_NSLOTS(c)) * kSlotWords + lane * 4);
     }
 }
 
 FPC_DEV void store_slot(const uint32_t* r, const Ctx& c, uint32_t slot) {
-    if (slot < c.nslots) {
+    if (slot < VM_NSLOTS(c)) {
 #if VM_SMEM_ASM
         const uint32_t a = c.sbase + slot * (kSlotWords * 4u);
 #pragma unroll
         for (int q = 0; q < 3; ++q) sts128(a + q * 512u, r + 4 * q);
 #else
-        store_col(c.slots + slot * kSlotWords + c.lane * 4, r);
+        store_col(c.slots + slot * kSlotWords + VM_LANE(c) * 4, r);
 #endif
     } else {
-        store_col(c.far + (slot - c.nslots) * kSlotWords + c.lane * 4, r);
+        store_col(VM_COLD(c).far + (slot - VM_NSLOTS(c)) * kSlotWords + VM_LANE(c) * 4, r);
     }
 }
 
@@ -219,9 +265,9 @@ FPC_DEV void load_wire(uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t off16
 }
 
 FPC_DEV void store_wire(const uint32_t* r, const Ctx& c, uint32_t bufid, uint32_t off16, bool per_batch, bool word) {
-    if (per_batch ? (c.lane != 0) : !c.store_ok) return;
-    const Buffer& b = c.buf[bufid];
-    const size_t idx = per_batch ? (size_t)(c.batch) : (size_t)c.item;
+    if (per_batch ? (VM_LANE(c) != 0) : !ctx_store_ok(c)) return;
+    const Buffer& b = VM_COLD(c).buf[bufid];
+    const size_t idx = per_batch ? (size_t)(VM_COLD(c).batch) : (size_t)ctx_item(c);
     uint32_t* p = reinterpret_cast<uint32_t*>(b.base + idx * b.stride + off16 * 16u);
     if (word) { p[0] = r[0]; return; }
 #pragma unroll
@@ -247,12 +293,12 @@ FPC_DEV void load_one(uint32_t* r, const Ctx& c, uint32_t idx, uint32_t flags, u
 #pragma unroll
         for (int q = 0; q < 3; ++q) lds128(r + 4 * q, a + q * 16u);
 #else
-        const uint32_t* s = c.consts + idx * 12;
+        const uint32_t* s = VM_COLD(c).consts + idx * 12;
 #pragma unroll
         for (int k = 0; k < 12; ++k) r[k] = s[k];
 #endif
     } else {
-        load_slot(r, c, idx, (flags & F_XLANE) ? (c.lane ^ xmask) : c.lane);
+        load_slot(r, c, idx, (flags & F_XLANE) ? (VM_LANE(c) ^ xmask) : VM_LANE(c));
     }
 }
 
@@ -262,7 +308,7 @@ FPC_DEV void load_near(uint32_t* r, const Ctx& c, uint32_t slot) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) lds128(r + 4 * q, a + q * 512u);
 #else
-    load_col(r, c.slots + slot * kSlotWords + c.lane * 4);
+    load_col(r, c.slots + slot * kSlotWords + VM_LANE(c) * 4);
 #endif
 }
 
@@ -334,12 +380,187 @@ FPC_DEV uint32_t phase_clock() {
 #endif
 }
 
+// ---- result post-processing + store (shared by all record types) ----------------------------------------
+// gaux: [7:0] destination buffer id  [15:8] destination field  [31:24] constant index for H_PADCONST
+FPC_DEV void post_and_store(const Ctx& c, uint32_t* r, uint32_t hdr, uint32_t gaux, uint32_t dst) {
+    if (hdr & (H_POST_ISZERO | H_POST_GTHALF)) {
+        uint32_t flag;
+        if ((hdr & H_POST_ISZERO) && (hdr & H_POST_GTHALF)) {
+            flag = r[0] & 1u;  // parity (sgn0)
+        } else if (hdr & H_POST_ISZERO) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) any |= r[k];
+            flag = any ? 0u : 1u;
+        } else {
+            uint32_t t[12];
+            flag = fpc::sub12(t, fpc::kHalfP, r);  // borrow <=> r > (p-1)/2
+        }
+        fpc::zero12(r);
+        r[0] = flag;
+    }
+    if ((hdr & H_PADCONST) && !ctx_store_ok(c)) {
+        const uint32_t* s = VM_COLD(c).consts + (gaux >> 24) * 12;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = s[k];
+    }
+    if (hdr & H_DSTG) {
+        store_wire(r, c, gaux & 0xFF, (gaux >> 8) & 0xFF, (hdr & H_DSTBATCH) != 0, (hdr & H_DSTWORD) != 0);
+    } else {
+        store_slot(r, c, dst);
+    }
+}
+
+// r += operand(w), one slot at a time: at most ONE 12-word temporary is live next to r (a fused product has x, y and this
+// temporary in registers -- 36 words like any other product; building the second half with load_operand first would need 48)
+FPC_DEV void accumulate_operand(uint32_t* r, const Ctx& c, uint32_t w, uint32_t xmask) {
+    uint32_t t[12];
+    if (operand_is_near(w)) {
+        const uint32_t fast = (w & (F_SIMPLE << 24)) ? 0u : ((w >> 28) & 0x7);
+        load_near(t, c, w & 0xFF);
+        if (fast == 1 || fast == 4) fpc::neg_raw(t, t);       // -A ...
+        if (fast == 5) shl1_raw(t);                            // 2A
+        (void)fpc::add12(r, r, t);
+        if (fast >= 2 && fast <= 4) {
+            load_near(t, c, (w >> 8) & 0xFF);
+            if (fast != 2) fpc::neg_raw(t, t);                 // ... - B
+            (void)fpc::add12(r, r, t);
+        }
+        return;
+    }
+    const uint32_t a = w & 0xFF, b = (w >> 8) & 0xFF, flags = w >> 24;
+    if (flags & F_GLOBAL) {
+        load_wire(t, c, a, b, (w >> 16) & 0xF, (w >> 20) & 0xF);
+        (void)fpc::add12(r, r, t);
+        return;
+    }
+    const int ca = sext4(w >> 16), cb = sext4(w >> 20);
+    load_one(t, c, a, flags, xmask);
+    if (ca < 0) fpc::neg_raw(t, t);
+    scale_raw(t, ca < 0 ? -ca : ca);
+    (void)fpc::add12(r, r, t);
+    if (cb != 0) {
+        load_one(t, c, b, flags, xmask);
+        if (cb < 0) fpc::neg_raw(t, t);
+        scale_raw(t, cb < 0 ? -cb : cb);
+        (void)fpc::add12(r, r, t);
+    }
+}
+
+// ---- two-output record (OP_MAC2) -------------------------------------------------------------------------
+// acc += sum over `n` product entries starting at record word `wi` (advanced); fused entry pairs count as two entries
+template <class WordFn>
+FPC_DEV void mac_entries(fpc::Acc& A, const Ctx& c, WordFn W, uint32_t& wi, uint32_t n, uint32_t xmask) {
+    for (uint32_t t = 0; t < n; ++t) {
+        uint32_t x[12], y[12];
+        const uint32_t wx = W(wi), wy = W(wi + 1);
+        wi += 2;
+        load_operand_pair(x, y, c, wx, wy, xmask);
+        if (wx & (F_FUSE << 24)) {
+            const uint32_t wx2 = W(wi), wy2 = W(wi + 1);
+            wi += 2;
+            ++t;
+            if (wx2) accumulate_operand(x, c, wx2, xmask);
+            if (wy2) accumulate_operand(y, c, wy2, xmask);
+        }
+        fpc::acc_mac(A, x, y);
+    }
+}
+
+// In programs of the two-output format EVERY multiply-accumulate record uses this layout (a record with one result
+// sets H_SINGLE and only has group 0), so that the interpreter contains ONE multiply-accumulate loop body.
+template <class WordFn>
+FPC_DEV void exec_mac2(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W) {
+    const uint32_t dst0 = (hdr >> 8) & 0xFF, dst1 = (hdr >> 16) & 0xFF;
+    const bool shared = (aux & 1023u) != 0;   // any entries in the groups M or P
+    constexpr uint32_t xmask = 0;              // cross-lane operands only occur in epilogue-only records (one-output format)
+    uint32_t wi = 4;
+    // Four accumulation phases (S_M, S_P, dst0, dst1) around ONE multiply-accumulate loop.  Every phase starts its
+    // accumulator from the 24-word value `w` (zero, S_P + S_M, or S_P - S_M + K p^2): the 58-register accumulator is
+    // never live across a phase boundary, only these 24 words are.
+    uint32_t w[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) w[k] = 0;
+#pragma unroll 1
+    for (uint32_t ph = shared ? ((aux & 31u) ? 0u : 1u) : 2u; ph < 4u; ++ph) {
+        fpc::Acc A;
+        fpc::acc_from_wide(A, w);
+        const uint32_t n = (aux >> (5u * ph)) & 31u;
+        mac_entries(A, c, W, wi, n, xmask);
+        if (ph == 0u) {            // S_M -> the 24-word scratch formed by the two destination slots
+            fpc::acc_collapse(A, w);
+            store_slot(w, c, dst0);
+            store_slot(w + 12, c, dst1);
+#pragma unroll
+            for (int k = 0; k < 24; ++k) w[k] = 0;
+        } else if (ph == 1u) {     // S_P; combine with S_M
+            uint32_t wp[24];
+            fpc::acc_collapse(A, wp);
+            if (aux & 31u) {
+                uint32_t wm[24];
+                load_slot(wm, c, dst0, VM_LANE(c));
+                load_slot(wm + 12, c, dst1, VM_LANE(c));
+                fpc::add24(w, wp, wm);                        // S_P + S_M: start of the dst0 accumulation
+                fpc::add24(wp, wp, fpc::kKP2[W(2) & 127u]);   // S_P + K p^2 - S_M >= 0: start of the dst1 accumulation
+                fpc::sub24(wp, wp, wm);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 24; ++k) w[k] = wp[k];
+            }
+            store_slot(wp, c, dst0);
+            store_slot(wp + 12, c, dst1);
+        } else {
+            const uint32_t sh = ph == 2u ? 0u : 1u;   // which output
+            uint32_t r[12];
+            if (shared || n) {
+                fpc::acc_redc(A, r);
+                const uint32_t ps = (W(2) >> (8u + 4u * sh)) & 7u;
+                if (ps > 1) scale_raw(r, (int)ps);
+            } else {
+                fpc::zero12(r);
+            }
+            const uint32_t E = (aux >> (20u + 2u * sh)) & 3u;
+            for (uint32_t e = 0; e < E; ++e) {
+                uint32_t z[12];
+                load_operand(z, c, W(52u + 2u * sh + e), xmask);
+                (void)fpc::add12(r, r, z);
+            }
+            fpc::correct(r, (int)((aux >> (24u + 3u * sh)) & 7u));
+            if (ph == 2u) {
+                if (hdr & H_SINGLE) {   // one result: flags, padding constant, global / slot store
+                    post_and_store(c, r, hdr, W(3), dst0);
+                    return;
+                }
+                if (shared) {   // fetch S_P - S_M + K p^2 before dst0 (half of the scratch) is overwritten
+                    load_slot(w, c, dst0, VM_LANE(c));
+                    load_slot(w + 12, c, dst1, VM_LANE(c));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 24; ++k) w[k] = 0;
+                }
+                store_slot(r, c, dst0);
+            } else {
+                store_slot(r, c, dst1);
+#pragma unroll
+                for (int k = 0; k < 24; ++k) w[k] = 0;   // `w` is (re)defined on EVERY path to the loop head: it is dead during
+                                                         // the multiply-accumulate instead of being kept in 24 registers
+            }
+        }
+    }
+}
+
+// Interpreter flavours: a program is either in the one-output format of round 1 (MODE_LEGACY: OP_MAC records) or in the
+// two-output format (MODE_MAC2: every multiply-accumulate is an OP_MAC2 record); each kernel instantiation contains one
+// multiply-accumulate body.  MODE_BOTH (CPU emulation) accepts either.
+enum : int { MODE_LEGACY = 0, MODE_MAC2 = 1, MODE_BOTH = 2 };
+
 // TRACE: ph[0..4] receive the cycles spent in operand loads, multiply-accumulates, the Montgomery reduction,
 // epilogue + correction, and the store (debug tracing only; the normal instantiation has no clock reads)
-template <bool TRACE = false, class WordFn>
+template <bool TRACE = false, int MODE = MODE_BOTH, class WordFn>
 FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W, uint32_t* ph = nullptr) {
     const uint32_t op = hdr & 0xFF;
     if (op == OP_NOP) return;
+    if (MODE != MODE_LEGACY && op == OP_MAC2) { exec_mac2(c, hdr, aux, W); return; }
     const uint32_t dst = (hdr >> 8) & 0xFF;
     const uint32_t T = (hdr >> 16) & 0xF;
     const uint32_t E = (hdr >> 20) & 0x3;
@@ -367,7 +588,7 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W, uin
         const uint32_t byte = p[nbytes - 1 - (bit >> 3)];
         fpc::zero12(r);
         r[0] = (byte >> (bit & 7)) & 1u;
-    } else if (T > 0) {
+    } else if (MODE != MODE_MAC2 && T > 0) {
         fpc::Acc A;
         fpc::acc_zero(A);
         uint32_t nwx = W(2), nwy = W(3);
@@ -406,32 +627,7 @@ FPC_DEV void exec_record(const Ctx& c, uint32_t hdr, uint32_t aux, WordFn W, uin
     fpc::correct(r, ncorr);
     uint32_t k4 = 0;
     if (TRACE) { k4 = phase_clock() + (r[11] & 0u); ph[3] += k4 - k3; }
-    if (hdr & (H_POST_ISZERO | H_POST_GTHALF)) {
-        uint32_t flag;
-        if ((hdr & H_POST_ISZERO) && (hdr & H_POST_GTHALF)) {
-            flag = r[0] & 1u;  // parity (sgn0)
-        } else if (hdr & H_POST_ISZERO) {
-            uint32_t any = 0;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) any |= r[k];
-            flag = any ? 0u : 1u;
-        } else {
-            uint32_t t[12];
-            flag = fpc::sub12(t, fpc::kHalfP, r);  // borrow <=> r > (p-1)/2
-        }
-        fpc::zero12(r);
-        r[0] = flag;
-    }
-    if ((hdr & H_PADCONST) && !c.store_ok) {
-        const uint32_t* s = c.consts + (aux >> 24) * 12;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) r[k] = s[k];
-    }
-    if (hdr & H_DSTG) {
-        store_wire(r, c, aux & 0xFF, (aux >> 8) & 0xFF, (hdr & H_DSTBATCH) != 0, (hdr & H_DSTWORD) != 0);
-    } else {
-        store_slot(r, c, dst);
-    }
+    post_and_store(c, r, hdr, aux, dst);
     if (TRACE) ph[4] += phase_clock() - k4;
 }
 

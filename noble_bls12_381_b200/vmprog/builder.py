@@ -27,11 +27,15 @@ R_MOD_P = R % P
 R2_MOD_P = R * R % P
 P_OVER_R = P / R  # ~0.1016
 
-OP_NOP, OP_MAC, OP_SEL, OP_BIT, OP_INV = 0, 1, 2, 3, 4
-F_CONST, F_GLOBAL, F_XLANE, F_SIMPLE = 1, 2, 4, 8
+OP_NOP, OP_MAC, OP_SEL, OP_BIT, OP_INV, OP_MAC2 = 0, 1, 2, 3, 4, 5
+F_CONST, F_GLOBAL, F_XLANE, F_SIMPLE, F_FUSE = 1, 2, 4, 8, 0x80
+H_SINGLE = 1 << 24
 H_BAR, H_DSTG, H_DSTWORD, H_DSTBATCH, H_PADCONST, H_POST_ISZERO, H_POST_GTHALF = 1 << 25, 1 << 26, 1 << 27, 1 << 28, 1 << 29, 1 << 30, 1 << 31
-REC_WORDS = 32
+REC_WORDS = 64
+WAIT_WORD = 60  # words 60..63: progress requirements
 MAX_TERMS = 12
+MAX_ENTRIES2 = 24  # product entries of a two-output record (a fused entry pair counts as two)
+MAX_KP2 = 63  # largest K of the device table of K*p^2 (csrc/fp_core_gen.cuh: kKP2)
 MAX_SUM_BOUND = 80.0  # sum of |x|*|y| bounds in units of p^2 that fits the 768-bit accumulator
 COST_MODEL = "v2"  # "v1" = the instruction-count estimate used before the trace calibration
 MAX_K = 9.5  # result bound (units of p): must stay below 2^384 / p = 9.84; `correct` handles up to 4 rounds
@@ -182,6 +186,14 @@ class Op:
     per_batch: bool = False  # global store by lane 0 at index item/32
     pad_const: Val | None = None  # padding lanes (item >= n_items) produce this constant instead
     after: list = field(default_factory=list)  # extra ordering deps (Ops)
+    # two-output record (kind == "mac2"): out / out2 are the two results; groups M, P, 0, 1 of product entries
+    # [(Operand x, Operand y, x2 | None, y2 | None)]: dst0 = ps0*redc(P + M + G0) + epi, dst1 = ps1*redc(P - M + G1) + epi2
+    out2: Val | None = None
+    groups: dict = field(default_factory=dict)
+    epi2: list = field(default_factory=list)
+    ncorr2: int = 0
+    post_scale2: int = 1
+    kp2: int = 0
     step: int = -1
     warp: int = -1
     sidx: int = -1
@@ -200,6 +212,12 @@ class Op:
             return (t + 1.7 if t else 0.6) + 0.1 * len(self.epi)
         if self.kind == "inv":
             return 114.0
+        if self.kind == "mac2":
+            ne = sum(len(g) for g in self.groups.values())
+            nf = sum(1 for g in self.groups.values() for e in g if e[2] is not None or e[3] is not None)
+            shared = 1 if (self.groups.get("M") or self.groups.get("P")) else 0
+            return (ne + 0.15 * nf + 2 * 1.1 + 0.45 + 0.3 * shared + (0.15 if self.groups.get("M") else 0.0)
+                    + 0.65 * (len(self.epi) + len(self.epi2)) + 0.07 * (self.ncorr + self.ncorr2))
         if self.kind != "mac":
             return 0.4
         t = len(self.terms)
@@ -215,12 +233,44 @@ class Op:
             vs += e.vals()
         for o in self.sel:
             vs += o.vals()
+        for g in self.groups.values():
+            for x, y, x2, y2 in g:
+                for o in (x, y, x2, y2):
+                    if o is not None:
+                        vs += o.vals()
+        for e in self.epi2:
+            vs += e.vals()
         return vs
+
+    def outs(self):
+        return [v for v in (self.out, self.out2) if v is not None]
+
+    def n_products(self):
+        if self.kind == "mac2":
+            return sum(len(g) for g in self.groups.values())
+        return len(self.terms) if self.kind == "mac" else 0
+
+    def n_reductions(self):
+        if self.kind == "mac2":
+            return 2
+        return 1 if (self.kind == "mac" and self.terms) else 0
+
+
+# Two-output records (products shared by the two coefficients of an Fp2 value: Karatsuba without an extra reduction) are
+# an EXPERIMENT that lost on the B200 (profiles/r2_notes.md: 0.84 M pairings/s against 1.29 M for one-output records; the
+# multiplier is not the bottleneck, per-warp dependent-instruction latency is, and the 768-bit recombination adds more of
+# it than three saved products remove).  BLS381_VM_DUAL=1 builds the programs in that format for A/B runs.
+DUAL_DEFAULT = __import__("os").environ.get("BLS381_VM_DUAL", "0") == "1"
+SHARE_ENABLED = True  # False: coefficient pairs are materialised as independent records even if they share products (tuning)
+CURRENT_DUAL = True   # policy of the Builder created last (read by tower.E2 when it expands an Fp2 product)
 
 
 class Builder:
-    def __init__(self, warps=6):
+    def __init__(self, warps=6, dual=None):
+        global CURRENT_DUAL
         self.warps = warps
+        self.dual = DUAL_DEFAULT if dual is None else dual
+        CURRENT_DUAL = self.dual
         self.ops: list[Op] = []
         self.vals: list[Val] = []
         self.consts: list[int] = []  # integer values exactly as stored in the device table
@@ -496,6 +546,156 @@ class Builder:
         # sum the partial results
         return self.mat(sum((Lin.of(v) for v in partial[1:]), Lin.of(partial[0])))
 
+    # ---- two-output records ---------------------------------------------------------------------------
+    def mat_lin(self, e) -> Lin:
+        """Materialise unless the expression is structurally zero (kept symbolic so sparsity survives)."""
+        if isinstance(e, Lin) and e.is_zero():
+            return e
+        if isinstance(e, Quad) and not e.terms and e.lin.is_zero():
+            return Lin()
+        return Lin.of(self.mat(e))
+
+    def mat2(self, terms, l0: Lin, l1: Lin):
+        """Materialise the coefficient pair  (sum k0_i X_i Y_i + l0,  sum k1_i X_i Y_i + l1)  given as
+        terms = [(k0, k1, X: Lin, Y: Lin)].  Products with k0 != 0 and k1 != 0 are computed ONCE (two-output record,
+        csrc/vm.cuh OP_MAC2); without shared products the two coefficients become independent records."""
+        terms = [(k0, k1, x, y) for k0, k1, x, y in terms if (k0 or k1) and not x.is_zero() and not y.is_zero()]
+
+        def split():
+            t0 = [(k0, x, y) for k0, k1, x, y in terms if k0]
+            t1 = [(k1, x, y) for k0, k1, x, y in terms if k1]
+            return self.mat_lin(Quad(t0, l0) if t0 else l0), self.mat_lin(Quad(t1, l1) if t1 else l1)
+
+        if not (self.dual and SHARE_ENABLED and any(k0 and k1 for k0, k1, _, _ in terms)):
+            return split()
+        r = self._try_emit2(terms, l0, l1)
+        return r if r is not None else split()
+
+    def _halves(self, lin: Lin):
+        """Operand(s) for a Lin of up to four terms: [Operand] or [Operand, Operand] (summed on load, F_FUSE)."""
+        if self._fits_operand(lin):
+            return [self._operand(lin)]
+        items = list(lin.t.items())
+        if len(items) <= 4 and all(abs(c) <= 4 for _, c in items):
+            slots = [(v, c) for v, c in items if v.kind != "const"]
+            consts = [(v, c) for v, c in items if v.kind == "const"]
+            halves = []
+            for grp in (slots, consts):
+                for i in range(0, len(grp), 2):
+                    halves.append(Lin(dict(grp[i:i + 2])))
+            if len(halves) <= 2:
+                return [self._operand(h) for h in halves]
+        return [self._operand(Lin.of(self.mat(lin)))]
+
+    def _try_emit2(self, terms, l0: Lin, l1: Lin):
+        import math
+
+        def post_of(ks):
+            g = 0
+            for k in ks:
+                g = math.gcd(g, abs(k))
+            for cand in (4, 3, 2):
+                if g and g % cand == 0:
+                    return cand
+            return 1
+
+        ps0 = post_of([k0 for k0, _, _, _ in terms if k0])
+        ps1 = post_of([k1 for _, k1, _, _ in terms if k1])
+        groups = {"M": [], "P": [], "0": [], "1": []}
+
+        def add(cls, k, x, y):
+            gx = math.gcd(*[abs(c) for c in x.t.values()])
+            gy = math.gcd(*[abs(c) for c in y.t.values()])
+            x = Lin({v: c // gx for v, c in x.t.items()})
+            y = Lin({v: c // gy for v, c in y.t.items()})
+            k *= gx * gy
+            if k < 0:
+                x, k = -x, -k
+            while k > 0:
+                fx = 4 // max(abs(c) for c in x.t.values())
+                fy = 4 // max(abs(c) for c in y.t.values())
+                best = None
+                for dx in range(1, fx + 1):
+                    for dy in range(1, fy + 1):
+                        if dx * dy <= k:
+                            key = (dx * dy, -max(dx, dy))
+                            if best is None or key > best[0]:
+                                best = (key, dx, dy)
+                _, dx, dy = best
+                groups[cls].append((x.scale(dx), y.scale(dy)))
+                k -= dx * dy
+
+        for k0, k1, x, y in terms:
+            assert k0 % ps0 == 0 and k1 % ps1 == 0
+            a, c = k0 // ps0, k1 // ps1
+            if a and c:
+                sgn = 1 if a > 0 else -1
+                m = min(abs(a), abs(c)) * sgn
+                if (a > 0) == (c > 0):
+                    add("P", m, x, y)
+                    a, c = a - m, c - m
+                else:
+                    add("M", m, x, y)
+                    a, c = a - m, c + m
+            if a:
+                add("0", a, x, y)
+            if c:
+                add("1", c, x, y)
+        # operands (up to four slots each, summed on load)
+        enc = {}
+        nent = 0
+        bsum = {}
+        for cls, lst in groups.items():
+            out = []
+            b_ = 0.0
+            for x, y in lst:
+                hx, hy = self._halves(x), self._halves(y)
+                x2 = hx[1] if len(hx) > 1 else None
+                y2 = hy[1] if len(hy) > 1 else None
+                out.append((hx[0], hy[0], x2, y2))
+                nent += 2 if (x2 is not None or y2 is not None) else 1
+                bx = hx[0].bound() + (x2.bound() if x2 is not None else 0)
+                by = hy[0].bound() + (y2.bound() if y2 is not None else 0)
+                if bx > 9 or by > 9:
+                    return None
+                b_ += bx * by
+            enc[cls] = out
+            bsum[cls] = b_
+        if nent > MAX_ENTRIES2:
+            return None
+        K = int(math.ceil(bsum["M"] - 1e-9)) if enc["M"] else 0
+        if K > MAX_KP2:
+            return None
+        acc0 = bsum["P"] + bsum["M"] + bsum["0"]
+        acc1 = bsum["P"] + K + bsum["1"]
+        if acc0 > MAX_SUM_BOUND or acc1 > MAX_SUM_BOUND:
+            return None
+        res = []
+        for acc, ps, lin in ((acc0, ps0, l0), (acc1, ps1, l1)):
+            chunks = self._chunk_lin(lin)
+            if len(chunks) > 2:
+                chunks = self._chunk_lin(Lin.of(self.mat(lin)))
+            kb = ps * (acc * P_OVER_R + 1) + sum(ch.bound() for ch in chunks)
+            if kb > MAX_K - 0.01:
+                if not chunks:
+                    return None
+                # keep the epilogue out of the record: added by a later (lazy) consumer instead
+                return None
+            ncorr = 0
+            while (1 << ncorr) <= kb + 1e-9:
+                ncorr += 1
+            assert ncorr <= 4, kb
+            res.append(([self._operand(z) for z in chunks], ncorr))
+        op = self._new_op([], res[0][0], res[0][1])
+        op.kind = "mac2"
+        op.groups = enc
+        op.epi2, op.ncorr2 = res[1]
+        op.post_scale, op.post_scale2, op.kp2 = ps0, ps1, K
+        v2 = Val(len(self.vals), "op", op=op)
+        self.vals.append(v2)
+        op.out2 = v2
+        return Lin.of(op.out), Lin.of(v2)
+
     def _chunk_lin(self, lin: Lin):
         chunks = []
         slots = [(v, c) for v, c in lin.t.items() if v.kind != "const"]
@@ -560,6 +760,27 @@ class Builder:
 
         for op in self.ops:
             res = []
+            if op.kind == "mac2":
+                res2 = []
+                for lane in range(lanes):
+                    def prod(e):
+                        x, y, x2, y2 = e
+                        xv = ev_operand(x, lane, 0) + (ev_operand(x2, lane, 0) if x2 is not None else 0)
+                        yv = ev_operand(y, lane, 0) + (ev_operand(y2, lane, 0) if y2 is not None else 0)
+                        assert xv < R and yv < R
+                        return xv * yv
+                    S = {k: sum(prod(e) for e in g) for k, g in op.groups.items()}
+                    assert S["M"] <= op.kp2 * P * P
+                    a0 = S["P"] + S["M"] + S["0"]
+                    a1 = S["P"] - S["M"] + op.kp2 * P * P + S["1"]
+                    assert 0 <= a0 < R * R and 0 <= a1 < R * R
+                    r0 = a0 * rinv % P * op.post_scale + sum(ev_operand(e, lane, 0) for e in op.epi)
+                    r1 = a1 * rinv % P * op.post_scale2 + sum(ev_operand(e, lane, 0) for e in op.epi2)
+                    res.append(r0 % P)
+                    res2.append(r1 % P)
+                env[op.out.id] = res
+                env[op.out2.id] = res2
+                continue
             for lane in range(lanes):
                 if op.kind == "sel":
                     f, a_, b_ = (ev_operand(o, lane, op.xmask) for o in op.sel)
@@ -676,20 +897,20 @@ class Builder:
                 last_use[v.id] = max(last_use.get(v.id, -1), op.step)
                 readers.setdefault(v.id, []).append(op.id)
         self.readers = readers
-        defs = [op for op in self.ops if op.out is not None]
-        for op in defs:
-            last_use.setdefault(op.out.id, op.step)
+        defs = [(op, v) for op in self.ops for v in op.outs()]
+        for op, v in defs:
+            last_use.setdefault(v.id, op.step)
         npos = len(self.ops)
         far = set()
         uses = {vid: len(r) for vid, r in readers.items()}
 
         def pressure():
             delta = [0] * (npos + 2)
-            for op in defs:
-                if op.out.id in far:
+            for op, v in defs:
+                if v.id in far:
                     continue
                 delta[op.step] += 1
-                delta[last_use[op.out.id] + 1] -= 1
+                delta[last_use[v.id] + 1] -= 1
             cur, peak, at = 0, 0, 0
             for s_ in range(npos + 1):
                 cur += delta[s_]
@@ -699,9 +920,9 @@ class Builder:
 
         peak, at = pressure()
         while peak > nslots:
-            cands = [op for op in defs if op.out.id not in far and op.step <= at <= last_use[op.out.id]]
-            cands.sort(key=lambda op: (last_use[op.out.id] - op.step) / (1 + uses.get(op.out.id, 0)), reverse=True)
-            far.add(cands[0].out.id)
+            cands = [(op, v) for op, v in defs if v.id not in far and op.step <= at <= last_use[v.id]]
+            cands.sort(key=lambda ov: (last_use[ov[1].id] - ov[0].step) / (1 + uses.get(ov[1].id, 0)), reverse=True)
+            far.add(cands[0][1].id)
             peak, at = pressure()
         self.peak_slots = peak
         nslots = max(peak, 1)  # never reserve more shared memory than the program needs
@@ -712,13 +933,13 @@ class Builder:
         free_far = []
         nfar = 0
         busy = []  # heap of (last_use, slot, is_far)
-        self.prev_in_slot = {}  # op id -> value id previously held by the slot it writes
+        self.prev_in_slot = {}  # op id -> value ids previously held by the slots it writes
         cur_val = {}
-        for op in sorted(defs, key=lambda o: o.step):
+        for op, v in sorted(defs, key=lambda ov: ov[0].step):
             while busy and busy[0][0] < op.step:
                 lu, k, isfar = heapq.heappop(busy)
                 heapq.heappush(free_far if isfar else free_near, (lu, k))
-            vid = op.out.id
+            vid = v.id
             if vid in far:
                 if free_far:
                     _, k = heapq.heappop(free_far)
@@ -732,7 +953,7 @@ class Builder:
                 heapq.heappush(busy, (last_use[vid], k, False))
             slot_of[vid] = k
             if k in cur_val:
-                self.prev_in_slot[op.id] = cur_val[k]
+                self.prev_in_slot.setdefault(op.id, []).append(cur_val[k])
             cur_val[k] = vid
         self.nslots = nslots
         self.nfar = nfar
@@ -745,7 +966,7 @@ class Builder:
         """Per record: the progress each other warp must have reached (RAW on operands, WAR/WAW on the
         destination slot).  Requirements already implied by earlier records of the same warp are dropped."""
         W = self.warps
-        val_op = {op.out.id: op for op in self.ops if op.out is not None}
+        val_op = {v.id: op for op in self.ops for v in op.outs()}
         known = [[0] * W for _ in range(W)]
         self.waits = {}
         self.full_reqs = {}
@@ -757,8 +978,7 @@ class Builder:
                 req[y.warp] = max(req[y.warp], y.sidx + 1)
             for a in op.after:
                 req[a.warp] = max(req[a.warp], a.sidx + 1)
-            pv = self.prev_in_slot.get(i)
-            if pv is not None:
+            for pv in self.prev_in_slot.get(i, []):
                 y = val_op[pv]
                 req[y.warp] = max(req[y.warp], y.sidx + 1)
                 for zid in self.readers.get(pv, []):
@@ -775,7 +995,6 @@ class Builder:
     def check_hazards(self):
         """Vector-clock proof that the emitted waits order every RAW, WAR and WAW pair."""
         W = self.warps
-        val_op = {op.out.id: op for op in self.ops if op.out is not None}
         vc = {}  # op id -> vector clock after completion
         last_vc = [[0] * W for _ in range(W)]
         for i in self.order:
@@ -796,10 +1015,13 @@ class Builder:
         holder = {}
         for i in self.order:
             op = self.ops[i]
-            if op.out is not None:
-                holder[self.slot_of[op.out.id]] = op.out.id
             for v in op.src_vals():
                 assert holder.get(self.slot_of[v.id]) == v.id, "operand slot overwritten before use"
+            for v in op.outs():
+                holder[self.slot_of[v.id]] = v.id
+            if op.kind == "mac2":  # the destination slots are scratch while the record runs: no operand may live there
+                for v in op.src_vals():
+                    assert self.slot_of[v.id] not in (self.slot_of[op.out.id], self.slot_of[op.out2.id])
 
     def _enc_operand(self, o: Operand) -> int:
         if o.flags & F_GLOBAL:
@@ -833,9 +1055,27 @@ class Builder:
                 flags |= 5 << 4
         return a | (b << 8) | ((o.ca & 0xF) << 16) | ((o.cb & 0xF) << 20) | (flags << 24)
 
+    def _enc_waits(self, words, wt):
+        """Words 60..63: eight 16-bit progress requirements (warps 0..7), or ten 12-bit / twelve 10-bit fields."""
+        W = self.warps
+        if any(wt):
+            words[0] |= H_BAR  # "has waits"
+        if W <= 8:  # eight 16-bit fields
+            wt = wt + [0] * (8 - W)
+            assert max(wt) < 65536
+            for j in range(4):
+                words[WAIT_WORD + j] = wt[2 * j] | (wt[2 * j + 1] << 16)
+        else:  # W fields of 12 bits (W <= 10) or 10 bits (W = 12), little-endian over the four words
+            fw = 12 if W <= 10 else 10
+            assert max(wt) < (1 << fw)
+            big = 0
+            for k, v_ in enumerate(wt):
+                big |= v_ << (fw * k)
+            for j in range(4):
+                words[WAIT_WORD + j] = (big >> (32 * j)) & 0xFFFFFFFF
+
     def encode(self):
-        """Returns (prog: bytes [W][nrec][32 words], nrec).  Words 27, 29, 30, 31 hold eight 16-bit progress
-        requirements (warps 0..7)."""
+        """Returns (prog: bytes [W][nrec][64 words], nrec)."""
         W = self.warps
         assert W <= 12
         streams = []
@@ -845,7 +1085,65 @@ class Builder:
                 op = self.ops[i]
                 words = [0] * REC_WORDS
                 dst = 0 if op.dst_global is not None else self.slot_of[op.out.id]
-                opcode = {"mac": OP_MAC, "sel": OP_SEL, "bit": OP_BIT, "inv": OP_INV}[op.kind]
+                opcode = {"mac": OP_MAC, "sel": OP_SEL, "bit": OP_BIT, "inv": OP_INV, "mac2": OP_MAC2}[op.kind]
+                if op.kind == "mac2" or (self.dual and op.kind == "mac" and op.terms):
+                    # two-output format; a one-output multiply-accumulate is the H_SINGLE form (group 0 only)
+                    single = op.kind == "mac"
+                    groups = {"0": [(x, y, None, None) for x, y in op.terms]} if single else op.groups
+                    epi2, ncorr2, ps2, kp2 = ([], 0, 1, 0) if single else (op.epi2, op.ncorr2, op.post_scale2, op.kp2)
+                    words[0] = OP_MAC2 | (dst << 8) | ((0 if single else self.slot_of[op.out2.id]) << 16)
+                    if single:
+                        words[0] |= H_SINGLE
+                        if op.post == "iszero":
+                            words[0] |= H_POST_ISZERO
+                        elif op.post == "gthalf":
+                            words[0] |= H_POST_GTHALF
+                        elif op.post == "parity":
+                            words[0] |= H_POST_ISZERO | H_POST_GTHALF
+                        if op.dst_word:
+                            words[0] |= H_DSTWORD
+                        assert op.xmask == 0  # cross-lane operands only occur in epilogue-only records
+                        gaux = 0
+                        if op.dst_global is not None:
+                            words[0] |= H_DSTG
+                            gaux |= op.dst_global[0] | (op.dst_global[1] << 8)
+                            if op.per_batch:
+                                words[0] |= H_DSTBATCH
+                        if op.pad_const is not None:
+                            words[0] |= H_PADCONST
+                            gaux |= op.pad_const.cidx << 24
+                        words[3] = gaux
+                    else:
+                        assert not op.post and op.dst_global is None and op.pad_const is None and op.xmask == 0
+                    cnt = {}
+                    wi = 4
+                    for cls in ("M", "P", "0", "1"):
+                        n = 0
+                        for x, y, x2, y2 in groups.get(cls, []):
+                            fused = x2 is not None or y2 is not None
+                            words[wi] = self._enc_operand(x) | ((F_FUSE << 24) if fused else 0)
+                            words[wi + 1] = self._enc_operand(y)
+                            wi += 2
+                            n += 1
+                            if fused:
+                                words[wi] = self._enc_operand(x2) if x2 is not None else 0
+                                words[wi + 1] = self._enc_operand(y2) if y2 is not None else 0
+                                assert (x2 is None or words[wi] != 0) and (y2 is None or words[wi + 1] != 0)
+                                wi += 2
+                                n += 1
+                        cnt[cls] = n
+                    assert wi <= 4 + 2 * MAX_ENTRIES2 and max(cnt.values()) < 32
+                    assert len(op.epi) <= 2 and len(epi2) <= 2 and kp2 <= MAX_KP2
+                    words[1] = (cnt["M"] | (cnt["P"] << 5) | (cnt["0"] << 10) | (cnt["1"] << 15) | (len(op.epi) << 20)
+                                | (len(epi2) << 22) | (op.ncorr << 24) | (ncorr2 << 27))
+                    words[2] = kp2 | (op.post_scale << 8) | (ps2 << 12)
+                    for e, z in enumerate(op.epi):
+                        words[52 + e] = self._enc_operand(z)
+                    for e, z in enumerate(epi2):
+                        words[54 + e] = self._enc_operand(z)
+                    self._enc_waits(words, self.waits[i])
+                    recs.append(words)
+                    continue
                 hdr = opcode | (dst << 8) | (len(op.terms) << 16) | (len(op.epi) << 20) | (op.ncorr << 22)
                 if op.post == "iszero":
                     hdr |= H_POST_ISZERO
@@ -880,23 +1178,7 @@ class Builder:
                 elif op.kind == "bit":
                     buf, off16, nbytes, bitindex = op.bit
                     words[2], words[3], words[4] = buf | (off16 << 8), bitindex, nbytes
-                wt = self.waits[i]
-                if any(wt):
-                    words[0] |= H_BAR  # "has waits"
-                if W <= 8:  # eight 16-bit fields
-                    wt = wt + [0] * (8 - W)
-                    assert max(wt) < 65536
-                    words[27] = wt[0] | (wt[1] << 16)
-                    words[29] = wt[2] | (wt[3] << 16)
-                    words[30] = wt[4] | (wt[5] << 16)
-                    words[31] = wt[6] | (wt[7] << 16)
-                else:  # W fields of 12 bits (W <= 10) or 10 bits (W = 12), little-endian over words 27, 29, 30, 31
-                    fw = 12 if W <= 10 else 10
-                    assert max(wt) < (1 << fw)
-                    big = 0
-                    for k, v_ in enumerate(wt):
-                        big |= v_ << (fw * k)
-                    words[27], words[29], words[30], words[31] = [(big >> (32 * j)) & 0xFFFFFFFF for j in range(4)]
+                self._enc_waits(words, self.waits[i])
                 recs.append(words)
             streams.append(recs)
         nrec = max(len(s_) for s_ in streams)
@@ -904,7 +1186,7 @@ class Builder:
         for w in range(W):
             recs = streams[w] + [[OP_NOP] + [0] * (REC_WORDS - 1)] * (nrec - len(streams[w]))
             for words in recs:
-                blob += struct.pack("<32I", *words)
+                blob += struct.pack("<%dI" % REC_WORDS, *words)
         return bytes(blob), nrec
 
     def const_table(self) -> bytes:

@@ -1,7 +1,7 @@
 """Compiles the tower-VM programs into the binary images the C-ABI library loads (*.b2vm).
 
-image := header (8 x u32: magic 'B2VM', version, warps, nrec, nconst, nslots, nfar, reserved)
-         constant table (nconst x 12 u32, Montgomery form)    program (warps x nrec x 32 u32)
+image := header (8 x u32: magic 'B2VM', version, warps, nrec, nconst, nslots, nfar, staged-buffer mask | format bit 31)
+         constant table (nconst x 12 u32, Montgomery form)    program (warps x nrec x 64 u32)
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ import sys
 from . import curves, tower
 
 MAGIC = 0x4D563242  # 'B2VM'
-VERSION = 1
+VERSION = 2  # 64-word records, two-output records
 DEFAULT_WARPS = 8
 DEFAULT_SLOTS = 66  # + up to 9 KB of TMA input staging per CTA, two CTAs per SM
 
@@ -27,6 +27,14 @@ def image(b) -> bytes:
                     staged |= 1 << o.gl[0]
         if op.kind == "bit":
             staged |= 1 << op.bit[0]
+    for op in b.ops:  # wire-format operands of two-output records (entries of the H_SINGLE form are op.terms above)
+        for g in op.groups.values():
+            for ent in g:
+                for o in ent:
+                    if o is not None and o.flags & 2:
+                        staged |= 1 << o.gl[0]
+    if b.dual:
+        staged |= 1 << 31  # two-output record format: the library picks the MODE_MAC2 interpreter
     hdr = struct.pack("<8I", MAGIC, VERSION, b.warps, nrec, len(b.consts), b.nslots, b.nfar, staged)
     return hdr + b.const_table() + prog
 
@@ -44,12 +52,20 @@ ALL_PROGRAMS = dict(tower.PROGRAMS)
 ALL_PROGRAMS.update(curves.PROGRAMS)
 
 
-def compile_program(name: str, warps=None, nslots=None):
+def compile_program(name: str, warps=None, nslots=None, dual=None):
+    """dual: None = the build default (builder.DUAL_DEFAULT); True / False = two-output / one-output record format."""
+    from . import builder as _b
     if warps is None:
         warps = INGEST_WARPS.get(name, DEFAULT_WARPS)
     if nslots is None:
         nslots = INGEST_SLOTS.get(name, DEFAULT_SLOTS)
-    b = ALL_PROGRAMS[name](warps)
+    prev = _b.DUAL_DEFAULT
+    if dual is not None:
+        _b.DUAL_DEFAULT = dual
+    try:
+        b = ALL_PROGRAMS[name](warps)
+    finally:
+        _b.DUAL_DEFAULT = prev
     b.schedule()
     b.allocate(nslots)
     b.check_hazards()

@@ -12,6 +12,7 @@ bit-identical to the reference's even though the *evaluation strategy* is differ
 """
 from __future__ import annotations
 
+from . import builder as _builder
 from .builder import Builder, Lin, Quad, Val, P
 
 X_PARAM = 0xD201000000010000  # |x| (math.ts:48); the curve parameter is negative
@@ -23,54 +24,126 @@ def _zero():
 
 def _mat(b: Builder, e):
     """Materialise unless the expression is structurally zero (kept symbolic so sparsity survives)."""
-    if isinstance(e, Lin) and e.is_zero():
-        return e
-    if isinstance(e, Quad) and not e.terms and e.lin.is_zero():
-        return Lin()
-    return Lin.of(b.mat(e))
+    return b.mat_lin(e)
+
+
+KARATSUBA_FP2 = True  # Fp2 products as three Fp products that feed BOTH coefficients (two-output records)
+SHARE = True          # switched off around latency-critical code: a shared product serialises the two coefficients on one warp
+SHARE_POLICY = __import__("os").environ.get("BLS381_VM_SHARE", "all")  # all | miller | none  (tuning)
+if SHARE_POLICY == "none":
+    SHARE = False
+    _builder.SHARE_ENABLED = False
+
+
+class no_sharing:
+    """Context manager: Fp2 products built inside are expanded without shared products (one record per coefficient)."""
+
+    def __enter__(self):
+        global SHARE
+        self.prev, SHARE = SHARE, False
+        _builder.SHARE_ENABLED = False
+
+    def __exit__(self, *a):
+        global SHARE
+        SHARE = self.prev
+        _builder.SHARE_ENABLED = self.prev
+
 
 
 class E2:
-    """Fp2 element c0 + c1*u whose coefficients are lazy expressions (Lin or Quad)."""
+    """Lazy Fp2 element  sum_i (k0_i + k1_i u) X_i Y_i + (l0 + l1 u):  products of Fp expressions with a weight for each
+    of the two coefficients, plus a linear part.  A product with k0 != 0 and k1 != 0 is SHARED by the two coefficients: it
+    is computed once by a two-output record (Builder.mat2).  `E2(c0, c1)` accepts Lin or Quad coefficients; `.c0` / `.c1`
+    give the coefficients back (Lin when the element is materialised / linear, else a Quad)."""
 
-    __slots__ = ("c0", "c1")
+    __slots__ = ("terms", "l0", "l1")
 
-    def __init__(self, c0, c1):
-        self.c0, self.c1 = c0, c1
+    def __init__(self, c0=None, c1=None, terms=None):
+        self.terms = list(terms) if terms else []
+        self.l0, self.l1 = Lin(), Lin()
+        for idx, c in ((0, c0), (1, c1)):
+            if c is None:
+                continue
+            if isinstance(c, Quad):
+                for k, x, y in c.terms:
+                    self.terms.append((k, 0, x, y) if idx == 0 else (0, k, x, y))
+                lin = c.lin
+            else:
+                lin = Lin.of(c)
+            if idx == 0:
+                self.l0 = lin
+            else:
+                self.l1 = lin
+
+    @staticmethod
+    def _raw(terms, l0, l1):
+        e = E2()
+        e.terms = [t for t in terms if (t[0] or t[1])]
+        e.l0, e.l1 = l0, l1
+        return e
+
+    @property
+    def c0(self):
+        t = [(k0, x, y) for k0, _, x, y in self.terms if k0]
+        return Quad(t, self.l0) if t else self.l0
+
+    @property
+    def c1(self):
+        t = [(k1, x, y) for _, k1, x, y in self.terms if k1]
+        return Quad(t, self.l1) if t else self.l1
+
+    def is_lin(self):
+        return not self.terms
 
     def __add__(self, o):
-        return E2(self.c0 + o.c0, self.c1 + o.c1)
-
-    def __sub__(self, o):
-        return E2(self.c0 - o.c0, self.c1 - o.c1)
+        return E2._raw(self.terms + o.terms, self.l0 + o.l0, self.l1 + o.l1)
 
     def __neg__(self):
-        return E2(-self.c0, -self.c1)
+        return E2._raw([(-k0, -k1, x, y) for k0, k1, x, y in self.terms], -self.l0, -self.l1)
+
+    def __sub__(self, o):
+        return self + (-o)
 
     def scale(self, k: int):
-        return E2(self.c0 * k, self.c1 * k)
+        return E2._raw([(k0 * k, k1 * k, x, y) for k0, k1, x, y in self.terms], self.l0 * k, self.l1 * k)
 
     def conj(self):
-        return E2(self.c0, -self.c1)
+        return E2._raw([(k0, -k1, x, y) for k0, k1, x, y in self.terms], self.l0, -self.l1)
 
     def mul_xi(self):  # * (1 + u)   (math.ts:471-475)
-        return E2(self.c0 - self.c1, self.c0 + self.c1)
+        return E2._raw([(k0 - k1, k0 + k1, x, y) for k0, k1, x, y in self.terms], self.l0 - self.l1, self.l0 + self.l1)
+
+    def _need_lin(self):
+        if self.terms:
+            raise TypeError("cannot multiply an unmaterialised Fp2 product; call .m(builder) first")
 
     def __mul__(self, o):
         if isinstance(o, int):
             return self.scale(o)
-        if isinstance(o, E2):  # (math.ts:451-462), schoolbook so that it stays one MAC per coefficient
-            return E2(self.c0 * o.c0 - self.c1 * o.c1, self.c0 * o.c1 + self.c1 * o.c0)
-        return E2(self.c0 * o, self.c1 * o)  # by an Fp expression
+        self._need_lin()
+        a0, a1 = self.l0, self.l1
+        if isinstance(o, E2):  # (math.ts:451-462)
+            o._need_lin()
+            b0, b1 = o.l0, o.l1
+            if KARATSUBA_FP2 and SHARE and SHARE_POLICY != "none" and _builder.CURRENT_DUAL and not (a0.is_zero() or a1.is_zero() or b0.is_zero() or b1.is_zero()):
+                # c0 = a0 b0 - a1 b1 ; c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1: three products, two of them shared
+                return E2._raw([(1, -1, a0, b0), (-1, -1, a1, b1), (0, 1, a0 + a1, b0 + b1)], Lin(), Lin())
+            t = [(1, 0, a0, b0), (-1, 0, a1, b1), (0, 1, a0, b1), (0, 1, a1, b0)]
+            return E2._raw([(k0, k1, x, y) for k0, k1, x, y in t if not x.is_zero() and not y.is_zero()], Lin(), Lin())
+        o = Lin.of(o)  # by an Fp expression
+        return E2._raw([(1, 0, a0, o), (0, 1, a1, o)], Lin(), Lin())
 
     def sqr(self):  # (math.ts:477-484)
-        return E2((self.c0 + self.c1) * (self.c0 - self.c1), (self.c0 * 2) * self.c1)
+        self._need_lin()
+        a0, a1 = self.l0, self.l1
+        return E2._raw([(1, 0, a0 + a1, a0 - a1), (0, 2, a0, a1)], Lin(), Lin())
 
     def m(self, b: Builder):
-        return E2(_mat(b, self.c0), _mat(b, self.c1))
+        v0, v1 = b.mat2(self.terms, self.l0, self.l1)
+        return E2(v0, v1)
 
     def is_zero(self):
-        return isinstance(self.c0, Lin) and isinstance(self.c1, Lin) and self.c0.is_zero() and self.c1.is_zero()
+        return not self.terms and self.l0.is_zero() and self.l1.is_zero()
 
 
 def e2_zero():
@@ -279,6 +352,9 @@ class Tower:
 
     # ---- final exponentiation (math.ts:856-874) ---------------------------------------------------
     def final_exponentiate(self, f: E12) -> E12:
+        if SHARE_POLICY == "miller" and SHARE:
+            with no_sharing():
+                return self.final_exponentiate(f)
         b = self.b
         f = f.m(b)
         t0 = (self.frob12_map(f, 6) * self.fp12_inv(f).m(b)).m(b)  # f^(p^6) / f

@@ -51,7 +51,7 @@ int vm_emu_run(const uint32_t* prog, int warps, int nrec, const uint32_t* consts
                 const uint32_t* rec = prog + ((size_t)w * nrec + pc[w]) * vm::kRecWords;
                 bool ok = true;
                 if (rec[0] & vm::H_BAR) {
-                    const uint32_t ww[4] = {rec[27], rec[29], rec[30], rec[31]};
+                    const uint32_t ww[4] = {rec[vm::kWaitWord], rec[vm::kWaitWord + 1], rec[vm::kWaitWord + 2], rec[vm::kWaitWord + 3]};
                     const int fw = warps <= 8 ? 16 : (warps <= 10 ? 12 : 10);  // field width, as in vm_kernel.cu
                     const unsigned __int128 big = ((unsigned __int128)ww[3] << 96) | ((unsigned __int128)ww[2] << 64) |
                                                   ((unsigned __int128)ww[1] << 32) | ww[0];
@@ -69,17 +69,16 @@ int vm_emu_run(const uint32_t* prog, int warps, int nrec, const uint32_t* consts
             else if (policy == 1) w = runnable.back();
             else { rng = rng * 1664525u + 1013904223u; w = runnable[(rng >> 16) % runnable.size()]; }
             const uint32_t* rec = prog + ((size_t)w * nrec + pc[w]) * vm::kRecWords;
+            vm::Cold cold;
+            memset(&cold, 0, sizeof(cold));
+            cold.nslots = (uint32_t)nslots; cold.far = far.data(); cold.consts = consts; cold.stage = nullptr;
+            cold.n_items = (uint32_t)n_items; cold.batch = (uint32_t)batch;
+            for (int i = 0; i < vm::kMaxBuffers; ++i) cold.buf[i] = buf[i];
             for (uint32_t lane = 0; lane < 32; ++lane) {
                 vm::Ctx c;
-                c.slots = slots.data(); c.consts = consts; c.far = far.data(); c.nslots = nslots;
-                c.lane = lane;
-                uint32_t item = batch * 32 + lane;
-                c.store_ok = item < (uint32_t)n_items;
-                c.item = c.store_ok ? item : (uint32_t)n_items - 1;
-                c.buf = buf;
-                c.batch = batch;
-                c.stage = nullptr; c.stage_off = nullptr;
-                vm::exec_record(c, rec[0], rec[1], [&](uint32_t i) { return rec[i]; });
+                c.slots = slots.data(); c.cold = &cold;
+                c.lane = lane; c.sbase = 0; c.cbase = 0;
+                vm::exec_record<false, vm::MODE_BOTH>(c, rec[0], rec[1], [&](uint32_t i) { return rec[i]; });
             }
             ++pc[w];
         }

@@ -79,7 +79,7 @@ def test_programs_schedule_and_slots(programs):
         # image size is consistent
         img = vmcompile.image(b)
         nrec = int.from_bytes(img[12:16], "little")
-        assert len(img) == 32 + 48 * len(b.consts) + b.warps * nrec * 128
+        assert len(img) == 32 + 48 * len(b.consts) + b.warps * nrec * 256
 
 
 def test_pairing_program_bit_exact_on_emulator(programs):
@@ -180,3 +180,26 @@ def test_synth_matches_oracle_multiples():
         q = O.pt_to_affine(O.G2, O.pt_multiply_unsafe(O.G2, O.G2_BASE, i + 1))
         assert g1[96 * i : 96 * i + 96] == p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
         assert g2[192 * i : 192 * i + 192] == b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+
+
+@pytest.mark.parametrize("name", ["pairing", "final_exp"])
+def test_two_output_record_format_on_emulator(name, golden_dir):
+    """The experimental two-output record format (shared products, OP_MAC2: csrc/vm.cuh) computes the same bytes: the
+    pairing program against the reference's kilic vectors, finalExponentiate against pairing.test.ts:65-96."""
+    b = vmcompile.compile_program(name, dual=True)
+    b.check_hazards()
+    assert any(op.kind == "mac2" for op in b.ops)
+    assert sum(op.n_products() for op in b.ops) < 0.8 * sum(op.n_products() for op in vmcompile.compile_program(name, dual=False).ops)
+    if name == "pairing":
+        n = 33
+        g1, g2 = synth.multiples_wire(n)
+        out = bytearray(576 * n)
+        emu.run_program(b, {0: (bytearray(g1), 96), 1: (bytearray(g2), 192), 2: (out, 576)}, n)
+        assert bytes(out) == open(os.path.join(golden_dir, "pairing_kilic_1000.bin"), "rb").read()[: 576 * n]
+    else:
+        import json
+        k = json.load(open(os.path.join(golden_dir, "pairing_kats.json")))
+        fin = O.fp12_to_bytes(O.fp12_from_twelve([int(x, 16) for x in k["final_exp_in"]]))
+        out = bytearray(576)
+        emu.run_program(b, {3: (bytearray(fin), 576), 2: (out, 576)}, 1)
+        assert bytes(out) == b"".join(int(x, 16).to_bytes(48, "big") for x in k["final_exp_out"])
