@@ -111,14 +111,18 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(total: int):
+def cpu_baseline(total: int, g1=None, g2=None):
     """The reference's algorithm on all host cores: the plain-C port of math.ts/index.ts (oracle/c, 64-bit limbs,
     the reference's own Karatsuba tower formulas; pinned to the reference's golden vectors), one thread per core,
-    on `total` pairings of the bench workload.  Returns (pairings/s, cores, n)."""
+    on `total` pairings of the bench workload (the first `total` pairs of the GPU arm's batch when given: kilic prefix +
+    random pairs; else (i G1, i G2)).  Returns (pairings/s, cores, n)."""
     from noble_bls12_381_b200 import synth
     from oracle import c_oracle
     cores = os.cpu_count() or 1
-    g1, g2 = synth.multiples_wire(total)
+    if g1 is None or len(g1) < 96 * total:
+        g1, g2 = synth.multiples_wire(total)
+    else:
+        g1, g2 = g1[: 96 * total], g2[: 192 * total]
     w = min(total, cores * 32)
     c_oracle.pairing_batch(g1[: 96 * w], g2[: 192 * w], w, True, cores)  # warm-up: tables + CPU clocks
     wall = None
@@ -163,106 +167,196 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def verify_section(eng, n, rank, world, dist, torch):
-    """BASELINE configs 3-5 at `n` signatures per GPU: sign n messages on the device (config 4), aggregate, then
-    time verifyBatch of the (world x n)-item batch sharded by index with ONE all-gather of the partial Fp12
-    products (config 5; world = 1 is config 3).  Host buffers in, verdict out: this is an end-to-end number."""
-    import hashlib
+def _oracle_threads(world):
+    return max(1, (os.cpu_count() or 1) // max(world, 1))
+
+
+def sign_section(eng, n, args):
+    """BASELINE config 4: n signatures (hash-to-curve G2 + constant-time scalar multiplication + compression) on one GPU,
+    through the C ABI with host buffers.  Inputs: the reference's 559 `priv:msg:sig` KATs as prefix, then seeded
+    random keys / 32-byte messages.  Parity: the KAT prefix against the fixture file and a strided sample (or, with
+    --full-parity, every signature) against the C oracle."""
+    import ctypes
+    from noble_bls12_381_b200 import synth
+    dst = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
+    kats = [l.split(":") for l in open(os.path.join(ROOT, "tests", "golden", "sign_g2_vectors.txt")).read().split("\n") if l]
+    t0 = time.time()
+    sks, msgs = synth.signing_inputs(n, 0x5167, kats)
+    packed, off = eng._pack(msgs)
+    t_gen = time.time() - t0
+    out = ctypes.create_string_buffer(96 * n)
+    w = min(n, 4096)
+    eng.sign_batch(sks[: 32 * w], msgs[:w], dst)  # warm-up (program load)
+    best = None
+    reps = 3
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc = eng.lib.bls381_sign_batch(sks, packed, off, n, dst, len(dst), out)
+        dt = time.perf_counter() - t0
+        assert rc == 0, eng.lib.bls381_last_error()
+        best = dt if best is None else min(best, dt)
+        kernel_ms = eng.last_kernel_ms()
+    sigs = out.raw
+    nk = min(n, len(kats))
+    kat_ok = sum(sigs[96 * i: 96 * i + 96].hex() == kats[i][2].strip().lower() for i in range(nk))
+    # C oracle (checker): every signature with --full-parity, else a strided sample
+    from oracle import c_oracle
+    if args.full_parity:
+        idx = list(range(n))
+    else:
+        k = min(n, args.sign_check)
+        idx = sorted(set([(j * n) // k for j in range(k)] + list(range(min(n, 64)))))
+    t0 = time.time()
+    ref = c_oracle.sign_batch(b"".join(sks[32 * i: 32 * i + 32] for i in idx), [msgs[i] for i in idx], dst)
+    t_ref = time.time() - t0
+    n_ok = sum(ref[96 * j: 96 * j + 96] == sigs[96 * i: 96 * i + 96] for j, i in enumerate(idx))
+    cores = os.cpu_count() or 1
+    return {
+        "metric": "sign sigs/sec (config 4: hash_to_curve G2 + privKey * H(m) + toSignature, host buffers through the C ABI)",
+        "value": n / best, "unit": "sigs/s", "n": n, "ms": best * 1e3, "kernel_ms": kernel_ms, "kernel_value": n / (kernel_ms * 1e-3),
+        "parity": {"kats_ok": kat_ok, "kats": nk, "n_ok": n_ok, "n": len(idx), "checked": "all" if args.full_parity else "strided sample + first 64",
+                   "checker": "oracle/c (pinned on the 559 reference KATs)"},
+        "cpu_baseline": {"value": len(idx) / t_ref, "unit": "sigs/s", "cores": cores, "kind": "port", "per_core": len(idx) / t_ref / cores,
+                         "sample": f"{len(idx)} signatures of the same batch on {cores} host threads (plain-C port of index.ts:746-752)"},
+        "input_generation_s": t_gen,
+    }
+
+
+def verify_section(eng, n, rank, world, dist, torch, tag, controls=True, check_single_gpu=False):
+    """verifyBatch on a (world x n)-item batch sharded by index, n items per GPU (BASELINE config 3 at world = 1 with
+    n = 262 144; config 5 at world = 8).  SURVEY 8d inputs: sk_i seeded, msg_i 32 distinct bytes, pk_i = getPublicKey(sk_i),
+    sig_i = sign(msg_i, sk_i), agg = aggregateSignatures(sigs) -- all produced by the engine (the C oracle checks a sample).
+    Timed: host buffers in, verdict out.  world = 1: ONE C-ABI call (bls381_verify_batch).  world > 1: every rank runs
+    bls381_verify_batch_partial_dev on its shard, ONE all-gather of the device-resident W x 576-byte partial products
+    (NCCL), product + final exponentiation on every rank (bls381_fp12_product_dev): no host bounce."""
+    import ctypes
     import numpy as np
     from noble_bls12_381_b200 import dist as bdist
     from noble_bls12_381_b200 import synth
     dst = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
-    P_ = synth.P
-    # keys sk_i = i + 1 on every rank (public keys (i+1)*G1 from the host-side synthetic generator); the messages
-    # are distinct per (rank, i), so the world x n batch has world x n different (message, signature) pairs
-    g1 = synth.g1_multiples_wire(n)
-    pks = []
-    for i in range(n):
-        x = int.from_bytes(g1[96 * i: 96 * i + 48], "big")
-        y = int.from_bytes(g1[96 * i + 48: 96 * i + 96], "big")
-        pks.append((x + ((y * 2) // P_) * (1 << 381) + (1 << 383)).to_bytes(48, "big"))
-    msgs = [hashlib.sha256(b"msg" + rank.to_bytes(2, "big") + i.to_bytes(8, "big")).digest() for i in range(n)]
-    sks = b"".join((i + 1).to_bytes(32, "big") for i in range(n))
+    seed = 0xBA7C4
+    t0 = time.time()
+    sks, msgs = synth.signing_inputs(n, seed, None, first=rank * n)   # global item index = rank * n + i
+    packed, off = eng._pack(msgs)
+    t_gen = time.time() - t0
+    pks = eng.get_public_key_batch(sks)
+    pk_ms = eng.last_kernel_ms()
     eng.sign_batch(sks[: 32 * 64], msgs[:64], dst)  # warm-up (program load)
-    sign_s = agg_s = None
+    sigs = eng.sign_batch(sks, msgs, dst)
+    agg_s = None
     for _ in range(2):  # best of two: the first full-size call also grows the library's staging / scratch buffers
-        t0 = time.perf_counter()
-        sigs = eng.sign_batch(sks, msgs, dst)
-        dt = time.perf_counter() - t0
-        sign_s = dt if sign_s is None else min(sign_s, dt)
-        sign_kernel_ms = eng.last_kernel_ms()
         t0 = time.perf_counter()
         agg, st = eng.aggregate_g2(sigs, n)
         dt = time.perf_counter() - t0
         agg_s = dt if agg_s is None else min(agg_s, dt)
+    t0 = time.perf_counter()
+    agg_pk, _ = eng.aggregate_g1(pks[: 48 * min(n, 2048)], min(n, 2048))  # test/benchmark.js:94 aggregatePublicKeys/2048
+    agg_pk_s = time.perf_counter() - t0
+    # sample check of the generated inputs against the C oracle
+    from oracle import c_oracle
+    k = min(n, 256)
+    gen_ok = (c_oracle.get_public_key_batch(sks[: 32 * k]) == pks[: 48 * k]) and (c_oracle.sign_batch(sks[: 32 * k], msgs[:k], dst) == sigs[: 96 * k])
     if world > 1:  # global aggregate signature = sum of the per-rank aggregates (set-up, untimed)
         t = torch.frombuffer(bytearray(agg), dtype=torch.uint8).cuda()
         outs = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(outs, t)
         agg, _ = eng.aggregate_g2(b"".join(bytes(o.cpu().numpy().tobytes()) for o in outs), world)
-    be = bdist.EngineBackend(eng)
-    import ctypes
-    # host buffers in the C ABI's own input format (packed messages + offsets, concatenated keys)
-    packed = b"".join(msgs)
-    off = (ctypes.c_uint64 * (n + 1))(*range(0, 32 * (n + 1), 32))
-    pk_cat = b"".join(pks)
-    out576 = ctypes.create_string_buffer(576)
     st_buf = (ctypes.c_int32 * (n + 1))()
     sig_arg = agg if rank == 0 else None
     np_ = n + (1 if rank == 0 else 0)
-
     verdict = ctypes.c_int(0)
+    stream = torch.cuda.current_stream()
+    # device-side exchange buffers: 576-byte partial + one status-level byte, padded to 640
+    mine = torch.zeros(640, dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros(640 * world, dtype=torch.uint8, device="cuda")
+    parts = torch.zeros(576 * world, dtype=torch.uint8, device="cuda")
+    result = torch.zeros(576, dtype=torch.uint8, device="cuda")
+    lvl_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
 
-    def run():
+    def run(msg_buf=packed, pk_buf=pks, sig=agg):
+        """-> verdict (1 true, 0 false, -1 the reference would throw)"""
         if world == 1:  # the fused single-GPU entry point: one C-ABI call, one synchronisation
-            rc = eng.lib.bls381_verify_batch(agg, packed, off, pk_cat, n, dst, len(dst), ctypes.byref(verdict), st_buf)
+            rc = eng.lib.bls381_verify_batch(sig, msg_buf, off, pk_buf, n, dst, len(dst), ctypes.byref(verdict), st_buf)
             assert rc == 0, eng.lib.bls381_last_error()
-            return verdict.value == 1
-        # every rank owns exactly its own n items (contiguous block `rank` of the world x n batch)
-        rc = eng.lib.bls381_verify_batch_partial(sig_arg, packed, off, pk_cat, n, dst, len(dst), out576, st_buf)
+            return verdict.value
+        rc = eng.lib.bls381_verify_batch_partial_dev(sig if rank == 0 else None, msg_buf, off, pk_buf, n, dst, len(dst), mine.data_ptr(), st_buf)
         assert rc == 0, eng.lib.bls381_last_error()
-        partial = out576.raw
-        lvl = bdist._level(np.frombuffer(st_buf, dtype=np.int32, count=np_))
-        parts = [partial]
-        if world > 1:
-            tt = torch.frombuffer(bytearray(partial) + bytearray([lvl, 0, 0, 0]), dtype=torch.uint8).cuda()
-            oo = [torch.empty_like(tt) for _ in range(world)]
-            dist.all_gather(oo, tt)  # the single exchange step (W x 580 bytes over NCCL)
-            raw = [bytes(o.cpu().numpy().tobytes()) for o in oo]
-            parts = [r[:576] for r in raw]
-            lvl = max(r[576] for r in raw)
-        res = be.combine(parts, True)
-        return (res == bdist.FP12_ONE) and lvl == 0
+        lvl_host[0] = bdist._level(np.frombuffer(st_buf, dtype=np.int32, count=np_))
+        mine[576:640].copy_(lvl_host, non_blocking=True)
+        dist.all_gather_into_tensor(gathered, mine)  # the single exchange step: W x 640 bytes, device to device (NCCL)
+        g2d = gathered.view(world, 640)
+        parts.view(world, 576).copy_(g2d[:, :576])
+        rc = eng.lib.bls381_fp12_product_dev(parts.data_ptr(), world, 1, result.data_ptr(), stream.cuda_stream)
+        assert rc == 0, eng.lib.bls381_last_error()
+        lvl = int(g2d[:, 576].max().item())
+        res = bytes(result.cpu().numpy().tobytes())
+        return -1 if lvl == 2 else (0 if lvl == 1 else (1 if res == bdist.FP12_ONE else 0))
 
-    ok = run()  # warm-up + correctness
+    ok = run() == 1  # warm-up + correctness
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    reps = 2
+    reps = 5
     t0 = time.perf_counter()
     for _ in range(reps):
-        ok = run() and ok
+        ok = (run() == 1) and ok
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt[0])
-    # negative control: one flipped message byte must give false
-    bad = list(msgs)
-    bad[n // 2] = bytes([bad[n // 2][0] ^ 1]) + bad[n // 2][1:]
-    k = min(n, 1024)
-    pos_partial, _ = be.partial(None, msgs[:k], b"".join(pks[:k]), dst)
-    bad2 = list(msgs[:k]); bad2[k // 2] = bad[n // 2]
-    neg_partial, _ = be.partial(None, bad2, b"".join(pks[:k]), dst)
-    return {
-        "metric": "verifyBatch sigs/sec (end to end, host buffers, sharded by index, one all-gather of W x 576 B)",
-        "value": world * n / dt, "unit": "sigs/s", "sigs_per_gpu": n, "n_gpus": world, "ms": dt * 1e3,
-        "verdict_true": bool(ok), "negative_control_differs": neg_partial != pos_partial,
-        "sign": {"value": n / sign_s, "unit": "sigs/s per GPU (host buffers)", "kernel_ms": sign_kernel_ms,
-                 "note": "hash-to-curve + constant-time G2 scalar multiplication + compression on device"},
-        "aggregate_signatures": {"value": n / agg_s, "unit": "sigs/s per GPU (decompress + validate + tree sum)"},
+    out = {
+        "metric": "verifyBatch sigs/sec (end to end, host buffers, sharded by index, one all-gather of W x 576 B device to device)",
+        "config": tag, "value": world * n / dt, "unit": "sigs/s", "sigs_per_gpu": n, "sigs_total": world * n, "n_gpus": world,
+        "ms": dt * 1e3, "reps": reps, "verdict_true": bool(ok), "inputs_match_c_oracle_sample": bool(gen_ok),
+        "aggregate_signatures": {"value": n / agg_s, "unit": "sigs/s per GPU (decompress + validate + tree sum)", "n": n},
+        "aggregate_public_keys_2048": {"ms": agg_pk_s * 1e3, "note": "test/benchmark.js:94; latency-bound single batch"},
+        "get_public_key": {"value": n / (pk_ms * 1e-3), "unit": "keys/s per GPU (kernel)"},
+        "input_generation_s": t_gen,
     }
+    if controls:
+        # negative controls AT CONFIG SIZE on this rank's shard (SURVEY 8d): every control is one more full call
+        ctl = {}
+        bad = bytearray(packed)
+        bad[32 * (n // 2)] ^= 1
+        ctl["flipped_message_byte"] = run(msg_buf=bytes(bad))
+        sw = bytearray(pks)
+        sw[0:48], sw[48 * (n - 1): 48 * n] = pks[48 * (n - 1): 48 * n], pks[0:48]
+        ctl["swapped_public_keys"] = run(pk_buf=bytes(sw))
+        inf = bytearray(pks)
+        inf[48 * (n // 3): 48 * (n // 3) + 48] = bytes([0xC0]) + bytes(47)
+        ctl["infinity_public_key"] = run(pk_buf=bytes(inf))
+        # an off-subgroup key is covered by the test suite (tests/test_gpu_ingest.py searches one);
+        # here: a key whose x has no square root -> the reference throws ("Invalid compressed G1 point")
+        junk = bytearray(pks)
+        junk[48 * (n // 5): 48 * (n // 5) + 48] = bytes([0x80]) + bytes(46) + b"\x07"  # x = 7: 7^3 + 4 is not a square
+        ctl["undecodable_public_key"] = run(pk_buf=bytes(junk))
+        if world > 1:
+            t = torch.tensor([ctl[k] for k in sorted(ctl)], dtype=torch.int32, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ctl = {k: int(v) for k, v in zip(sorted(ctl), t.tolist())}
+        ctl["expected"] = {"flipped_message_byte": 0, "swapped_public_keys": 0, "infinity_public_key": 0, "undecodable_public_key": -1}
+        ctl["ok"] = all(ctl[k] == v for k, v in ctl["expected"].items())
+        out["negative_controls"] = ctl
+    if check_single_gpu and world > 1:
+        # config 5: the sharded result equals the single-GPU result on the same data bit for bit -- compared on the
+        # UN-exponentiated 576 bytes: product of the W gathered partials vs ONE GPU running all world x n items
+        rc = eng.lib.bls381_verify_batch_partial_dev(sig_arg, packed, off, pks, n, dst, len(dst), mine.data_ptr(), st_buf)
+        assert rc == 0
+        dist.all_gather_into_tensor(gathered, mine)
+        parts.view(world, 576).copy_(gathered.view(world, 640)[:, :576])
+        raw = torch.zeros(576, dtype=torch.uint8, device="cuda")
+        assert eng.lib.bls381_fp12_product_dev(parts.data_ptr(), world, 0, raw.data_ptr(), stream.cuda_stream) == 0
+        sharded = bytes(raw.cpu().numpy().tobytes())
+        same = None
+        if rank == 0:
+            all_sks, all_msgs = synth.signing_inputs(world * n, seed, None, first=0)
+            all_pks = eng.get_public_key_batch(all_sks)
+            whole, st_all = eng.verify_batch_partial(agg, all_msgs, all_pks, dst)
+            same = (whole == sharded) and not np.any(st_all)
+        out["sharded_equals_single_gpu_bit_for_bit"] = same
+    return out
 
 
 def main():
@@ -274,8 +368,13 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--program-dir", default=None, help="alternative tower-VM program directory (tuning)")
-    ap.add_argument("--wide-per-product", type=int, default=144, help="IMAD.WIDE per 384x384 product of the built Fp core (108 for -DBLS381_KARATSUBA)")
-    ap.add_argument("--verify-n", type=int, default=262144, help="signatures per GPU for the verifyBatch / sign section: BASELINE config 3 (262 144 on one GPU; x8 GPUs = config 5); 0 = skip")
+    ap.add_argument("--wide-per-product", type=int, default=144, help="IMAD.WIDE per 384x384 product of the built Fp core")
+    ap.add_argument("--verify-n", type=int, default=262144, help="signatures per GPU for the verifyBatch section: BASELINE config 3 (262 144 on one GPU; x8 GPUs = config 5); 0 = skip")
+    ap.add_argument("--sign-n", type=int, default=1048576, help="signatures of the sign section (BASELINE config 4, one GPU); 0 = skip")
+    ap.add_argument("--sign-check", type=int, default=4096, help="signatures of the sign section compared with the C oracle (strided sample)")
+    ap.add_argument("--strong-total", type=int, default=2097152, help="total signatures of the strong-scaling verifyBatch row (config 5: fixed batch over 1/2/4/8 GPUs); 0 = skip")
+    ap.add_argument("--full-parity", action="store_true", help="compare EVERY signature of the sign section with the C oracle (minutes of CPU time)")
+    ap.add_argument("--parity-n", type=int, default=-1, help="pairings compared with the C oracle per GPU (-1 = all)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -295,9 +394,10 @@ def main():
     from noble_bls12_381_b200 import synth
     eng = bls.Engine(local_rank, args.program_dir)
     n = args.n
-    # synthetic inputs: (i*G1, i*G2); every rank processes its own n items (weak scaling, sharded by index)
+    # inputs: the reference's 1000 kilic pairs (i G1, i G2) as prefix, then P_i = a_i G1, Q_i = b_i G2
+    # with a_i, b_i from a SHA-256 counter-mode PRNG (seed 0xB200 + rank); every rank processes its own n items
     t_gen = time.time()
-    g1, g2 = synth.multiples_wire(n)
+    g1, g2 = synth.random_pairs_wire(eng, n, seed=0xB200 + rank, prefix=1000)
     t_gen = time.time() - t_gen
     h1 = torch.frombuffer(bytearray(g1), dtype=torch.uint8).pin_memory()
     h2 = torch.frombuffer(bytearray(g2), dtype=torch.uint8).pin_memory()
@@ -317,12 +417,6 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    # parity inside the bench: the first 1000 outputs are the reference's kilic fixtures
-    gold_path = os.path.join(ROOT, "tests", "golden", "pairing_kilic_1000.bin")
-    parity = None
-    if os.path.exists(gold_path):
-        k = min(n, 1000)
-        parity = bytes(dout[: 576 * k].cpu().numpy().tobytes()) == open(gold_path, "rb").read()[: 576 * k]
 
     sampler = ClockSampler()
     time.sleep(0.15)
@@ -339,11 +433,10 @@ def main():
     launches = eng.launch_count() - launches0
     ms_total = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    resident_out = bytes(dout.cpu().numpy().tobytes())
 
-    # end-to-end through the C-ABI host entry point (host buffers in, host buffers out)
-    import ctypes
-    e2e_steps = max(1, min(args.steps, 3))
-    out_buf = ctypes.create_string_buffer(576 * n)
+    # end-to-end through the C-ABI host entry point (pinned host buffers in, host buffers out, copies inside the timed region)
+    e2e_steps = max(3, args.steps)
     eng.lib.bls381_pairing_batch(h1.data_ptr(), h2.data_ptr(), n, 1, hout.data_ptr(), None)  # warm
     barrier()
     t0 = time.perf_counter()
@@ -354,21 +447,57 @@ def main():
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t_region1 = time.time()
     sampler.stop()
-    if parity:
-        k = min(n, 1000)
-        parity = bytes(hout[: 576 * k].numpy().tobytes()) == open(gold_path, "rb").read()[: 576 * k]
+    # the same with the reference's validity checks of every point (index.ts:717-718) on the device
+    st_arr = torch.empty(n, dtype=torch.int32).pin_memory()
+    eng.lib.bls381_pairing_batch(h1.data_ptr(), h2.data_ptr(), n, 1, hout.data_ptr(), st_arr.data_ptr())
+    t0 = time.perf_counter()
+    for _ in range(2):
+        rc = eng.lib.bls381_pairing_batch(h1.data_ptr(), h2.data_ptr(), n, 1, hout.data_ptr(), st_arr.data_ptr())
+        assert rc == 0
+    e2e_checked_s = (time.perf_counter() - t0) / 2
+    statuses_ok = bool((st_arr == 0).all().item())
 
-    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+    # ---- parity: EVERY output of the timed batch against the C oracle (checker; its threads are split over the ranks),
+    # the kilic prefix additionally against the reference's fixture file
+    e2e_out = bytes(hout.numpy().tobytes())
+    gold_path = os.path.join(ROOT, "tests", "golden", "pairing_kilic_1000.bin")
+    k = min(n, 1000)
+    fixtures_ok = (e2e_out[: 576 * k] == open(gold_path, "rb").read()[: 576 * k]) if os.path.exists(gold_path) else None
+    from oracle import c_oracle
+    pn = n if args.parity_n < 0 else min(n, args.parity_n)
+    t0 = time.time()
+    ref = c_oracle.pairing_batch(g1[: 96 * pn], g2[: 192 * pn], pn, True, _oracle_threads(world))
+    t_parity = time.time() - t0
+    n_ok = sum(ref[576 * i: 576 * i + 576] == e2e_out[576 * i: 576 * i + 576] == resident_out[576 * i: 576 * i + 576] for i in range(pn))
+
+    t = torch.tensor([ms_total, e2e_s, e2e_checked_s, float(n_ok), float(pn)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s = float(t[0]), float(t[1])
+        tm = t[:3].clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t[3:].clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        t = torch.cat([tm, ts])
+    ms_total, e2e_s, e2e_checked_s, n_ok_all, pn_all = [float(x) for x in t]
     ms_per_step = ms_total / args.steps
     value = world * n / (ms_per_step * 1e-3)
     e2e_value = world * n / e2e_s
 
-    vb = None
+    vb = vs = sg = None
     if args.verify_n > 0:
-        vb = verify_section(eng, args.verify_n, rank, world, dist if world > 1 else None, torch)
+        vb = verify_section(eng, args.verify_n, rank, world, dist if world > 1 else None, torch,
+                            "config 3 (262 144 per GPU)" if world == 1 else "config 3 sized shards, weak scaling (config 5 at 8 GPUs)",
+                            controls=True, check_single_gpu=False)
+    if args.strong_total > 0 and args.strong_total // world != args.verify_n:
+        vs = verify_section(eng, args.strong_total // world, rank, world, dist if world > 1 else None, torch,
+                            "config 5: %d signatures in total, strong scaling" % args.strong_total, controls=False, check_single_gpu=(world > 1))
+    elif args.strong_total > 0 and vb is not None:
+        vs = dict(vb, config="config 5: %d signatures in total, strong scaling (same run as the weak row at this GPU count)" % args.strong_total)
+        if world > 1:
+            chk = verify_section(eng, min(args.verify_n, 32768), rank, world, dist, torch, "bit-for-bit check", controls=False, check_single_gpu=True)
+            vs["sharded_equals_single_gpu_bit_for_bit"] = chk.get("sharded_equals_single_gpu_bit_for_bit")
+            vs["sharded_equals_single_gpu_note"] = "checked on %d signatures per GPU" % min(args.verify_n, 32768)
+    if args.sign_n > 0 and world == 1:
+        sg = sign_section(eng, args.sign_n, args)
 
     if rank == 0:
         peaks = {}
@@ -379,17 +508,23 @@ def main():
         imad_peak = eng.imad_peak()
         imad_sustained, imad_sustained_mhz = eng.imad_peak_sustained(1.0)
         prog_dir = args.program_dir or os.path.join(ROOT, "noble_bls12_381_b200", "programs")
-        IMAD_ISSUED_PER_PAIRING, n_products, n_reductions = issued_imad_per_item(os.path.join(prog_dir, "pairing.b2vm"), args.wide_per_product)
+
+        def issued(name):
+            return issued_imad_per_item(os.path.join(prog_dir, name + ".b2vm"), args.wide_per_product)
+
+        IMAD_ISSUED_PER_PAIRING, n_products, n_reductions = issued("pairing")
         per_gpu = n / (ms_per_step * 1e-3)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
             "metric": "pairings/sec", "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "config 2: %d independent pairings e(i*G1, i*G2) per GPU, Miller loop + final exponentiation, bit-exact vs kilic fixtures" % n,
+            "config": {"workload": "config 2: %d independent pairings per GPU on random (a_i G1, b_i G2) (SHA-256 counter-mode scalars, seed 0xB200 + rank; the reference's 1000 kilic pairs as prefix), Miller loop + final exponentiation, every output byte-compared" % n,
                        "items_per_step_per_gpu": n, "parallelism": "shard-by-index x%d, no collective" % world,
                        "cache": "inputs+outputs+VM scratch (%.0f MB) are re-streamed every step; compute-bound kernel (0.9 KB/pairing), no L2 flush needed" % ((288 + 576) * n / 1e6)},
-            "parity_first_1000_vs_reference_fixtures": parity,
+            "parity": {"n_ok": int(n_ok_all), "n": int(pn_all), "checker": "oracle/c pairing (pinned on the reference fixtures), all ranks",
+                       "kilic_prefix_vs_reference_fixture_file": fixtures_ok, "seconds": t_parity},
+            "parity_first_1000_vs_reference_fixtures": fixtures_ok,
             "kernel_ms_per_step": kernel_ms,
             "roofline": {
                 "bound": "imad", "achieved": per_gpu * IMAD_PER_PAIRING / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
@@ -398,23 +533,56 @@ def main():
                 "frac_sustained": per_gpu * IMAD_PER_PAIRING / imad_sustained,
                 "issued_per_pairing": {"imad_wide": IMAD_ISSUED_PER_PAIRING, "products": n_products, "reductions": n_reductions},
                 "issued": per_gpu * IMAD_ISSUED_PER_PAIRING / 1e12, "issued_frac_sustained": per_gpu * IMAD_ISSUED_PER_PAIRING / imad_sustained,
-                "traffic": 3841792, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE vm_kernel launch over 9472 pairings (ncu --set full, profiles/r1_v8_ncu_summary.txt): the 2.7 MB algorithmic bytes plus the program image; results are still in L2 when the kernel ends.  The kernel is compute-bound: the HBM fraction is ~1e-4",
+                "traffic": 3841792, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE vm_kernel launch over 9472 pairings (ncu --set full): the 2.7 MB algorithmic bytes plus the program image; results are still in L2 when the kernel ends.  The kernel is compute-bound: the HBM fraction is ~1e-4",
                 "note": "integer-multiply pipe bound (SURVEY 8d): achieved = pairings/s/GPU x 15.4k Fp-mul x 288 IMAD; peak = IMAD.WIDE.U32 issue rate measured live on this GPU in a 3 ms burst (bls381_imad_peak, boost clock); peak_sustained = the same microbenchmark back to back for 1 s (power-settled clock, the fair denominator for a step this long); issued = the multiply-adds the kernel actually executes (lazy-reduction program: more products, fewer reductions)",
                 "hbm": {"achieved": per_gpu * BYTES_PER_PAIRING / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * BYTES_PER_PAIRING / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             },
-            "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": 288 * n, "d2h_bytes_per_step": 576 * n},
+            "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": 288 * n, "d2h_bytes_per_step": 576 * n, "steps": e2e_steps},
+            "e2e_with_validity_checks": {"value": world * n / e2e_checked_s, "unit": "pairings/s", "all_status_ok": statuses_ok,
+                                         "note": "bls381_pairing_batch with a status array: P.assertValidity() + Q.assertValidity() (index.ts:717-718) of every point on the device"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(t_region0, t_region1, kernel_mhz),
             "input_generation_s": t_gen,
         }
         if vb is not None:
             line["verify_batch"] = vb
+        if vs is not None:
+            line["verify_batch_strong"] = vs
+        if sg is not None:
+            line["sign"] = sg
+        # per-section issued-multiply rooflines (issued IMAD.WIDE of the program images / kernel time)
+        sect = {}
+        if sg is not None:
+            iw, pr, rd = issued("sign")
+            sect["sign"] = {"imad_wide_per_item": iw, "products": pr, "reductions": rd,
+                            "issued_frac_sustained": sg["kernel_value"] * iw / imad_sustained}
+        line["roofline_sections"] = sect
+        cpu = None
         if not args.no_cpu_baseline:
-            v, cores, cnt = cpu_baseline(max((os.cpu_count() or 1) * 1600, 4096))  # ~10 s of all-core CPU work in total
-            line["cpu_baseline"] = {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cnt} pairings of the same workload ({cnt // cores} per core), plain-C port of math.ts/index.ts (oracle/c, reference's Karatsuba tower formulas), one thread per core, outputs checked against the reference fixtures; the TypeScript original is ~43 pairings/s/core by its own comment (index.ts:719)"}
+            v, cores, cnt = cpu_baseline(max((os.cpu_count() or 1) * 1600, 4096), g1, g2)  # ~10 s of all-core CPU work in total
+            cpu = {"value": v, "unit": "pairings/s", "cores": cores, "kind": "port", "per_core": v / cores,
+                   "sample": f"{cnt} pairings of the same workload ({cnt // cores} per core), plain-C port of math.ts/index.ts (oracle/c, reference's Karatsuba tower formulas), one thread per core, outputs checked against the reference fixtures; the TypeScript original is ~43 pairings/s/core by its own comment (index.ts:719)"}
+            line["cpu_baseline"] = cpu
+        # BASELINE.md section 3 table shape
+        rows = [{"config": "2: independent pairings", "N": n * world, "GPUs": world, "rate": value, "unit": "pairings/s",
+                 "imad_per_s": per_gpu * world * IMAD_PER_PAIRING, "frac_of_measured_imad_peak": per_gpu * IMAD_PER_PAIRING / imad_peak,
+                 "hbm_gbs": per_gpu * world * BYTES_PER_PAIRING / 1e9, "bit_exact": "%d/%d" % (int(n_ok_all), int(pn_all)),
+                 "cpu_baseline": None if cpu is None else {"cores": cpu["cores"], "rate": cpu["value"], "per_core": cpu["per_core"]},
+                 "speed_up": None if cpu is None else value / cpu["value"]}]
+        if vb is not None:
+            rows.append({"config": "3/5 weak: verifyBatch", "N": vb["sigs_total"], "GPUs": world, "rate": vb["value"], "unit": "sigs/s",
+                         "bit_exact": "verdict %s, controls %s" % (vb["verdict_true"], (vb.get("negative_controls") or {}).get("ok"))})
+        if vs is not None:
+            rows.append({"config": "5 strong: verifyBatch", "N": vs["sigs_total"], "GPUs": world, "rate": vs["value"], "unit": "sigs/s",
+                         "bit_exact": "verdict %s, sharded == single GPU: %s" % (vs["verdict_true"], vs.get("sharded_equals_single_gpu_bit_for_bit"))})
+        if sg is not None:
+            rows.append({"config": "4: sign", "N": sg["n"], "GPUs": 1, "rate": sg["value"], "unit": "sigs/s",
+                         "bit_exact": "%d/%d KATs, %d/%d vs oracle" % (sg["parity"]["kats_ok"], sg["parity"]["kats"], sg["parity"]["n_ok"], sg["parity"]["n"]),
+                         "cpu_baseline": {"cores": sg["cpu_baseline"]["cores"], "rate": sg["cpu_baseline"]["value"], "per_core": sg["cpu_baseline"]["per_core"]},
+                         "speed_up": sg["value"] / sg["cpu_baseline"]["value"]})
+        line["table"] = rows
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

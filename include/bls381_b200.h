@@ -20,7 +20,10 @@
  *     (bad argument, CUDA error, library not initialised); bls381_last_error() has the text.
  *     Per-item conditions are reported through `status[i]` (BLS381_ST_*), so that the wrapper can
  *     re-create the reference's throw-vs-false behaviour (index.ts:716, :385-386, :635-636, :802-820).
- *   - The library never keeps caller pointers after a call returns.  Thread-safe per call.
+ *   - The library never keeps caller pointers after a call returns.  Thread-safe per call (calls are serialised per
+ *     device context).  `_dev` entry points are asynchronous on the caller's stream; their internal scratch (far slots,
+ *     partial products, product tree) is kept per stream, so calls on different streams do not share buffers.
+ *   - msg_off[0] must be 0 and msg_off non-decreasing (BLS381_EINVAL otherwise).
  *   - There is NO CPU fallback: every entry point fails with BLS381_ENODEV without a CUDA device.
  */
 #ifndef BLS381_B200_H
@@ -48,7 +51,7 @@ extern "C" {
 #define BLS381_ST_BAD_ENCODING 4    /* 'Invalid compressed G1 point', bad flags     index.ts:312 */
 #define BLS381_ST_NO_SQRT 5         /* 'Failed to find a square root'               index.ts:518 */
 
-/* Library lifetime.  `device` = CUDA ordinal.  `program_dir` = directory holding the tower-VM program
+/* Library lifetime.  `device` = CUDA ordinal (a second call with a different ordinal fails with BLS381_EINVAL).  `program_dir` = directory holding the tower-VM program
  * files (*.b2vm) produced at build time; NULL = "<dir of this shared object>/programs". */
 int bls381_init(int device, const char* program_dir);
 int bls381_shutdown(void);
@@ -58,8 +61,12 @@ int bls381_sm_count(void);
 
 /* pairing(P, Q, withFinalExponent)                               replaces index.ts:715-722
  * (the Miller loop math.ts:1331-1388 with fused line evaluation + finalExponentiate math.ts:856-874)
- * n independent pairings e(P_i, Q_i) of affine, valid, non-infinity points.
- *   g1  : n x 96 B,  g2 : n x 192 B,  out : n x 576 B,  status : n x int32 or NULL              */
+ * n independent pairings e(P_i, Q_i) of affine points.
+ *   g1  : n x 96 B,  g2 : n x 192 B,  out : n x 576 B
+ *   status : n x int32, filled in the reference's order of checks (index.ts:716-718): INFINITY if P_i or Q_i is the affine
+ *            image (0, 0) of the point at infinity (math.ts:955), else the result of P_i.assertValidity(), else that of
+ *            Q_i.assertValidity() (NOT_ON_CURVE / NOT_IN_SUBGROUP); the 576 output bytes of a failing item are zero.
+ *            NULL = the caller vouches for the points (e.g. they come from bls381_g1_decompress_batch): no checks run. */
 int bls381_pairing_batch(const uint8_t* g1, const uint8_t* g2, size_t n, int with_final_exp,
                          uint8_t* out_fp12, int32_t* status);
 /* same, device pointers, asynchronous on `cuda_stream` (a cudaStream_t cast to void*) */
@@ -105,6 +112,27 @@ int bls381_verify_batch(const uint8_t* sig96, const uint8_t* msgs, const uint64_
 int bls381_verify_batch_partial(const uint8_t* sig96_or_null, const uint8_t* msgs, const uint64_t* msg_off,
                                 const uint8_t* pks48, size_t n, const uint8_t* dst, size_t dst_len,
                                 uint8_t* out_fp12, int32_t* status);
+/* the same, the product stays in device memory (d_out_fp12 = device pointer): a multi-process run all-gathers the partials
+ * device to device and finishes with bls381_fp12_product_dev */
+int bls381_verify_batch_partial_dev(const uint8_t* sig96_or_null, const uint8_t* msgs, const uint64_t* msg_off,
+                                    const uint8_t* pks48, size_t n, const uint8_t* dst, size_t dst_len,
+                                    uint8_t* d_out_fp12, int32_t* status);
+
+/* In-process multi-GPU (north_star: "large verifyBatch workloads shard by signature index across the 8 GPUs of
+ * one box with a single all-reduce of the partial Gt products over NVLink").
+ *   bls381_init_devices(mask): one context per CUDA device whose bit is set (bit d = ordinal d); the first one is also
+ *   the context of every single-device entry point.  NCCL is loaded at run time (dlopen libnccl.so.2, ncclCommInitAll);
+ *   bls381_multi_transport() says "nccl" or, if that failed, "peer-copy" (cudaMemcpyPeer of the 576-byte partials).
+ *   bls381_verify_batch_multi: verifyBatch (index.ts:792-821) with the items sharded by index over the contexts (contiguous
+ *   blocks, one host thread per device), ONE all-gather of W x 576 bytes device to device -- NCCL has no modular-product
+ *   reduction op; gather + product is the all-reduce of this monoid -- then the product and ONE final exponentiation on the
+ *   first device.  Same arguments, verdict and status layout as bls381_verify_batch; same result bit for bit.        */
+int bls381_init_devices(uint32_t device_mask, const char* program_dir);
+int bls381_device_count(void);
+const char* bls381_multi_transport(void);
+int bls381_verify_batch_multi(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
+                              size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status);
+
 /* sign(message, privateKey) for byte messages                                   replaces index.ts:746-752
  * (hashToCurve + constant-time scalar multiplication math.ts:1061-1078 + toSignature index.ts:586-598).
  *   sks32: n x 32 B big-endian scalars already normalised to 0 < sk < r (normalizePrivKey index.ts:269-279 is
@@ -112,6 +140,11 @@ int bls381_verify_batch_partial(const uint8_t* sig96_or_null, const uint8_t* msg
  *   of the point at infinity); out_sig96: n x 96 B compressed signatures.                                   */
 int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
                       const uint8_t* dst, size_t dst_len, uint8_t* out_sig96);
+/* getPublicKey(privateKey)                                                      replaces index.ts:738-740 (351-353)
+ *   sks32: n x 32 B big-endian scalars (reduced mod r on the device without secret-dependent branches, like
+ *   normalizePrivKey index.ts:269-279; the reference's fixed-base wNAF table math.ts:1086-1167 yields the same point);
+ *   out48: n compressed public keys (sk = 0 mod r gives the encoding of the point at infinity; the wrapper rejects it). */
+int bls381_get_public_key_batch(const uint8_t* sks32, size_t n, uint8_t* out48);
 /* aggregatePublicKeys(Hex[]) / aggregateSignatures(Hex[])                       replaces index.ts:773-788
  *   n compressed points in, one compressed point out; status[i] per input (any status other than OK / INFINITY
  *   means the reference would have thrown while decoding that element).                                    */
@@ -131,6 +164,7 @@ int bls381_g1_scalar_mul_batch(const uint8_t* g1_affine, const uint8_t* scalars3
 /* prod_i f_i in Fp12 (+ optional finalExponentiate): combines the per-GPU partial products of a sharded
  * verifyBatch after the all-gather (index.ts:815-816).  in: n x 576 B, out: 576 B.                          */
 int bls381_fp12_product(const uint8_t* in_fp12, size_t n, int with_final_exp, uint8_t* out_fp12);
+int bls381_fp12_product_dev(const uint8_t* d_in_fp12, size_t n, int with_final_exp, uint8_t* d_out_fp12, void* cuda_stream);
 
 /* Generic tower-VM launch (used by the tests and by the entry points above).
  *   program  : name of a loaded program ("pairing", "miller", "final_exp", ...)

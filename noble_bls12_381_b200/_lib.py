@@ -48,6 +48,12 @@ def _load():
     lib.bls381_g2_validate_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_g1_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_g2_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_get_public_key_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_verify_batch_partial_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_fp12_product_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_init_devices.argtypes = [ctypes.c_uint32, ctypes.c_char_p]
+    lib.bls381_multi_transport.restype = ctypes.c_char_p
+    lib.bls381_verify_batch_multi.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     lib.bls381_verify_batch_partial.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_verify_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     return lib
@@ -62,6 +68,8 @@ EXPORTS = [
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
     "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
     "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_g1_scalar_mul_batch", "bls381_verify_batch_partial",
+    "bls381_get_public_key_batch", "bls381_verify_batch_partial_dev", "bls381_fp12_product_dev", "bls381_init_devices",
+    "bls381_device_count", "bls381_multi_transport", "bls381_verify_batch_multi",
 ]
 
 
@@ -153,6 +161,39 @@ class Engine:
         out = ctypes.create_string_buffer(96 * n)
         self._check(self.lib.bls381_sign_batch(sks32, packed, off, n, dst, len(dst), out))
         return out.raw
+
+    def get_public_key_batch(self, sks32: bytes) -> bytes:
+        """getPublicKey for n 32-byte big-endian scalars -> n x 48 B compressed public keys"""
+        n = len(sks32) // 32
+        assert len(sks32) == 32 * n
+        out = ctypes.create_string_buffer(48 * n)
+        self._check(self.lib.bls381_get_public_key_batch(sks32, n, out))
+        return out.raw
+
+    def pairing_batch_checked(self, g1: bytes, g2: bytes, n: int, with_final_exp: bool = True):
+        """pairing() with the reference's checks (index.ts:716-718) -> (n x 576 B, status list)"""
+        assert len(g1) == 96 * n and len(g2) == 192 * n
+        out = ctypes.create_string_buffer(576 * n)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_pairing_batch(g1, g2, n, int(with_final_exp), out, st))
+        return out.raw, list(st)
+
+    def init_devices(self, mask: int) -> int:
+        """one context per CUDA device in `mask` for verify_batch_multi; returns the number of contexts"""
+        self._check(self.lib.bls381_init_devices(mask, None))
+        return int(self.lib.bls381_device_count())
+
+    def multi_transport(self) -> str:
+        return self.lib.bls381_multi_transport().decode()
+
+    def verify_batch_multi(self, sig96: bytes, msgs, pks48: bytes, dst: bytes):
+        """verifyBatch sharded over every initialised device -> (verdict, status list of n + 1 codes)"""
+        n = len(msgs)
+        packed, off = self._pack(msgs)
+        v = ctypes.c_int(0)
+        st = (ctypes.c_int32 * (n + 1))()
+        self._check(self.lib.bls381_verify_batch_multi(sig96, packed, off, pks48, n, dst, len(dst), ctypes.byref(v), st))
+        return v.value, list(st)
 
     def aggregate_g1(self, pks48: bytes, n: int):
         out = ctypes.create_string_buffer(48)

@@ -104,3 +104,59 @@ def g1_multiples_wire(n: int):
     """g1_bytes n x 96 for i*G1, i = 1..n (the public keys of the secret keys 1..n)."""
     g1 = _multiples(_F1, (GX, GY), n, 3)
     return b"".join(x.to_bytes(48, "big") + y.to_bytes(48, "big") for x, y in g1)
+
+
+# ---- seeded random workloads (SURVEY section 8d) ------------------------------------------------------------------
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def random_scalars(n: int, seed: int, first: int = 0):
+    """(a, b): two n x 32-byte big-endian scalar arrays from a SHA-256 counter-mode PRNG: item i (counted from `first`) gets
+    SHA-256(seed || tag || i) mod r, a zero remapped to 1."""
+    import hashlib
+    s = seed.to_bytes(8, "big")
+
+    def gen(tag):
+        out = bytearray()
+        for i in range(first, first + n):
+            v = int.from_bytes(hashlib.sha256(s + tag + i.to_bytes(8, "big")).digest(), "big") % R_ORDER
+            out += (v or 1).to_bytes(32, "big")
+        return bytes(out)
+
+    return gen(b"a"), gen(b"b")
+
+
+def random_pairs_wire(eng, n: int, seed: int = 0xB200, prefix: int = 0):
+    """(g1 n x 96 B, g2 n x 192 B): the first `prefix` pairs are (i G1, i G2), i = 1..prefix (the reference's kilic fixtures,
+    test/deterministic.test.ts:34-46), the rest P_i = a_i G1, Q_i = b_i G2 with the scalars of random_scalars(seed).  The
+    random multiples are computed by the ENGINE's own scalar multiplication (the checker -- oracle/c -- only ever sees the
+    resulting bytes)."""
+    prefix = min(prefix, n)
+    g1p, g2p = multiples_wire(prefix) if prefix else (b"", b"")
+    m = n - prefix
+    if m == 0:
+        return g1p, g2p
+    a, b = random_scalars(m, seed, prefix)
+    base1 = (GX.to_bytes(48, "big") + GY.to_bytes(48, "big")) * m
+    base2 = b"".join(c.to_bytes(48, "big") for c in (G2X[0], G2X[1], G2Y[0], G2Y[1])) * m
+    g1, f1 = eng.g1_scalar_mul_batch(base1, a, m)
+    g2, f2 = eng.g2_scalar_mul_batch(base2, b, m)
+    assert not any(f1) and not any(f2)
+    return g1p + g1, g2p + g2
+
+
+def signing_inputs(n: int, seed: int, kats=None, first: int = 0):
+    """(sks n x 32 B, [messages]): optional `kats` = [(sk_hex, msg_hex, sig_hex)] lines of the reference's
+    test/bls12-381-g2-test-vectors.txt as prefix, then sk_i = SHA-256(seed || "sk" || i) (the engine reduces mod r),
+    msg_i = SHA-256(seed || "msg" || i) (32 bytes, distinct)."""
+    import hashlib
+    s = seed.to_bytes(8, "big")
+    sks = bytearray()
+    msgs = []
+    for sk, m, _ in (kats or [])[:n]:
+        sks += int(sk, 16).to_bytes(32, "big")
+        msgs.append(bytes.fromhex(m))
+    for i in range(first + len(msgs), first + n):
+        sks += hashlib.sha256(s + b"sk" + i.to_bytes(8, "big")).digest()
+        msgs.append(hashlib.sha256(s + b"msg" + i.to_bytes(8, "big")).digest())
+    return bytes(sks), msgs

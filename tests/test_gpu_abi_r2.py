@@ -1,0 +1,210 @@
+"""GPU tests of the C-ABI entry points added in round 2 (include/bls381_b200.h): per-item status of pairing()
+(index.ts:716-718), getPublicKey batches (index.ts:738-740) against the zkcrypto vectors, argument validation, the
+in-process multi-GPU verifyBatch, the device-resident partial products, and full-size byte compares against the C oracle."""
+import ctypes
+import hashlib
+import os
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DST = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from noble_bls12_381_b200 import _lib
+    return _lib.engine()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import noble_oracle
+    return noble_oracle
+
+
+def _wire1(p):
+    return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+
+
+def _wire2(q):
+    return b"".join(v.to_bytes(48, "big") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+
+
+def test_pairing_batch_status_follows_reference_order_of_checks(eng, O):
+    """index.ts:716-718: infinity of either point, then P.assertValidity(), then Q.assertValidity()."""
+    from noble_bls12_381_b200 import synth
+    n = 40
+    g1, g2 = synth.multiples_wire(n)
+    g1, g2 = bytearray(g1), bytearray(g2)
+    # 3: P = infinity; 5: Q = infinity; 7: P off curve; 9: Q off curve; 11: P on curve outside the subgroup;
+    # 13: Q outside the subgroup; 15: P off curve AND Q off curve (P is reported); 17: P infinity and Q off curve (infinity wins)
+    g1[96 * 3: 96 * 4] = bytes(96)
+    g2[192 * 5: 192 * 6] = bytes(192)
+    g1[96 * 7 + 95] ^= 1
+    g2[192 * 9 + 191] ^= 1
+    x = 1
+    while True:
+        x += 1
+        y = O.fp_sqrt((x**3 + 4) % O.P)
+        if y is not None and not O.g1_is_torsion_free((x, y, 1)):
+            break
+    g1[96 * 11: 96 * 12] = _wire1((x, y))
+    xx = (1, 1)
+    while True:
+        xx = (xx[0] + 1, xx[1])
+        yy = O.fp2_sqrt(O.fp2_add(O.fp2_pow(xx, 3), O.B2))
+        if yy is not None and not O.g2_is_torsion_free((xx, yy, O.FP2_ONE)):
+            break
+    g2[192 * 13: 192 * 14] = _wire2((xx, yy))
+    g1[96 * 15 + 95] ^= 1
+    g2[192 * 15 + 191] ^= 1
+    g1[96 * 17: 96 * 18] = bytes(96)
+    g2[192 * 17 + 191] ^= 1
+    out, st = eng.pairing_batch_checked(bytes(g1), bytes(g2), n, True)
+    want = {3: 1, 5: 1, 7: 2, 9: 2, 11: 3, 13: 3, 15: 2, 17: 1}
+    gold = open(os.path.join(GOLDEN, "pairing_kilic_1000.bin"), "rb").read()
+    for i in range(n):
+        assert st[i] == want.get(i, 0), i
+        if i in want:
+            assert out[576 * i: 576 * (i + 1)] == bytes(576), i
+        else:
+            assert out[576 * i: 576 * (i + 1)] == gold[576 * i: 576 * (i + 1)], i
+    # status == NULL: no checks, same bytes for the valid items
+    out2 = eng.pairing_batch(bytes(g1), bytes(g2), n, True)
+    assert all(out2[576 * i: 576 * (i + 1)] == gold[576 * i: 576 * (i + 1)] for i in range(n) if i not in want)
+
+
+def test_get_public_key_batch_matches_all_zkcrypto_g1_vectors(eng):
+    """test/zkcrypto g1_compressed: entry i = i * G1 compressed (deterministic.test.ts:49-64), all 999 non-zero entries."""
+    g1c = open(os.path.join(GOLDEN, "zkcrypto_g1_compressed.dat"), "rb").read()
+    pks = eng.get_public_key_batch(b"".join(i.to_bytes(32, "big") for i in range(1, 1000)))
+    assert pks == g1c[48:]
+    # scalars are reduced mod r (normalizePrivKey); 0 mod r gives the encoding of ZERO
+    ks = [R_ORDER + 5, 2 * R_ORDER + 9, (1 << 256) - 1, R_ORDER]
+    got = eng.get_public_key_batch(b"".join(k.to_bytes(32, "big") for k in ks))
+    from oracle import c_oracle as C
+    for j, k in enumerate(ks[:3]):
+        assert got[48 * j: 48 * j + 48] == C.get_public_key_batch((k % R_ORDER).to_bytes(32, "big")), j
+    assert got[48 * 3: 48 * 4] == g1c[:48]
+
+
+def test_bad_message_offsets_are_rejected(eng):
+    n = 4
+    msgs = b"abcdefgh"
+    out = ctypes.create_string_buffer(192 * n)
+    for off in ([1, 2, 4, 6, 8], [0, 4, 2, 6, 8]):
+        arr = (ctypes.c_uint64 * (n + 1))(*off)
+        assert eng.lib.bls381_hash_to_g2_batch(msgs, arr, n, DST, len(DST), out) == -1  # BLS381_EINVAL
+        sig = ctypes.create_string_buffer(96 * n)
+        assert eng.lib.bls381_sign_batch(bytes(32 * n), msgs, arr, n, DST, len(DST), sig) == -1
+    arr = (ctypes.c_uint64 * (n + 1))(0, 2, 4, 6, 8)
+    assert eng.lib.bls381_hash_to_g2_batch(None, arr, n, DST, len(DST), out) == -1  # null buffer, non-empty messages
+
+
+def _signed_batch(eng, n, seed=b"r2"):
+    sks = b"".join(hashlib.sha256(seed + b"sk" + i.to_bytes(4, "big")).digest() for i in range(n))
+    msgs = [hashlib.sha256(seed + b"m" + i.to_bytes(4, "big")).digest()[: 1 + i % 32] for i in range(n)]
+    pks = eng.get_public_key_batch(sks)
+    sigs = eng.sign_batch(sks, msgs, DST)
+    agg, st = eng.aggregate_g2(sigs, n)
+    assert all(s == 0 for s in st)
+    return sks, msgs, pks, sigs, agg
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 64, 95, 97, 1000])
+def test_verify_batch_any_size_including_padded_miller_products(eng, n):
+    """n + 1 Miller loops with n + 1 mod 3 = 0, 1, 2: the batch is padded with neutral pairs instead of a second launch."""
+    sks, msgs, pks, sigs, agg = _signed_batch(eng, n)
+    v, st = eng.verify_batch(agg, msgs, pks, DST)
+    assert v == 1 and all(s == 0 for s in st)
+    bad = list(msgs)
+    bad[n // 2] = bad[n // 2] + b"!"
+    assert eng.verify_batch(agg, bad, pks, DST)[0] == 0
+    if n >= 2:
+        swapped = pks[48:96] + pks[:48] + pks[96:]
+        assert eng.verify_batch(agg, msgs, swapped, DST)[0] == 0
+
+
+def test_keys_and_signatures_match_the_c_oracle(eng):
+    from oracle import c_oracle as C
+    n = 300
+    sks, msgs, pks, sigs, agg = _signed_batch(eng, n, b"oracle")
+    assert pks == C.get_public_key_batch(sks)
+    assert sigs == C.sign_batch(sks, msgs, DST)
+
+
+def test_device_resident_partials_combine_to_the_fused_verdict(eng):
+    """bls381_verify_batch_partial_dev + bls381_fp12_product_dev: the multi-process exchange path without a host bounce."""
+    import torch
+    n = 200
+    sks, msgs, pks, sigs, agg = _signed_batch(eng, n, b"dev")
+    cuts = [0, 70, 131, 200]
+    parts = torch.zeros(3 * 576, dtype=torch.uint8, device="cuda")
+    for j in range(3):
+        lo, hi = cuts[j], cuts[j + 1]
+        packed, off = eng._pack(msgs[lo:hi])
+        st = (ctypes.c_int32 * (hi - lo + 1))()
+        rc = eng.lib.bls381_verify_batch_partial_dev(agg if j == 0 else None, packed, off, pks[48 * lo: 48 * hi], hi - lo, DST, len(DST),
+                                                     parts.data_ptr() + 576 * j, st)
+        assert rc == 0 and all(s == 0 for s in st)
+    out = torch.zeros(576, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream()
+    assert eng.lib.bls381_fp12_product_dev(parts.data_ptr(), 3, 1, out.data_ptr(), s.cuda_stream) == 0
+    torch.cuda.synchronize()
+    one = bytes(47) + b"\x01" + bytes(528)
+    assert bytes(out.cpu().numpy().tobytes()) == one
+    # the un-exponentiated product of the three shards equals the one of the whole batch (Fp12 products are exact)
+    raw = torch.zeros(576, dtype=torch.uint8, device="cuda")
+    assert eng.lib.bls381_fp12_product_dev(parts.data_ptr(), 3, 0, raw.data_ptr(), s.cuda_stream) == 0
+    torch.cuda.synchronize()
+    whole, _ = eng.verify_batch_partial(agg, msgs, pks, DST)
+    assert bytes(raw.cpu().numpy().tobytes()) == whole
+
+
+def test_verify_batch_multi_in_process(eng):
+    """bls381_init_devices + bls381_verify_batch_multi: every visible GPU takes a contiguous shard; with one GPU the call
+    is the single-device one.  Verdict and status words equal the single-device call."""
+    import torch
+    ndev = torch.cuda.device_count()
+    assert eng.init_devices((1 << ndev) - 1) == ndev
+    n = 1037
+    sks, msgs, pks, sigs, agg = _signed_batch(eng, n, b"multi")
+    v1, st1 = eng.verify_batch(agg, msgs, pks, DST)
+    vm, stm = eng.verify_batch_multi(agg, msgs, pks, DST)
+    assert (v1, st1) == (1, [0] * (n + 1)) and (vm, stm) == (v1, st1)
+    bad = list(msgs)
+    bad[n - 1] = b"x" + bad[n - 1]
+    assert eng.verify_batch_multi(agg, bad, pks, DST)[0] == 0
+    inf_pk = pks[:48 * 500] + bytes([0xC0]) + bytes(47) + pks[48 * 501:]
+    vm, stm = eng.verify_batch_multi(agg, msgs, inf_pk, DST)
+    assert vm == 0 and stm[500] == 1
+    junk = pks[:48 * 900] + bytes([0x80]) + bytes(46) + b"\x07" + pks[48 * 901:]  # x = 7: x^3 + 4 has no square root
+    vm, stm = eng.verify_batch_multi(agg, msgs, junk, DST)
+    assert vm == -1 and stm[900] != 0
+    assert eng.multi_transport() in ("nccl", "peer-copy", "single-device")
+    if ndev > 1:
+        assert eng.multi_transport() in ("nccl", "peer-copy")
+
+
+def test_random_pairs_config2_sample_vs_c_oracle(eng):
+    """SURVEY 8d config 2 at test size: P_i = a_i G1, Q_i = b_i G2 from a SHA-256 counter-mode PRNG (seed 0xB200), every
+    output byte-compared with the C oracle (bench.py does the same at 65 536)."""
+    from noble_bls12_381_b200 import synth
+    from oracle import c_oracle as C
+    n = 4096
+    g1, g2 = synth.random_pairs_wire(eng, n, seed=0xB200)
+    # the generator itself (device scalar multiplications of the base points) against the oracle's
+    a, b = synth.random_scalars(n, 0xB200)
+    o1, o2 = C.scalar_mul_bases_batch(a[: 32 * 64], b[: 32 * 64])
+    assert g1[: 96 * 64] == o1 and g2[: 192 * 64] == o2
+    out = eng.pairing_batch(g1, g2, n, True)
+    assert out == C.pairing_batch(g1, g2, n, True)
+    raw = eng.pairing_batch(g1[: 96 * 512], g2[: 192 * 512], 512, False)
+    assert raw == C.pairing_batch(g1[: 96 * 512], g2[: 192 * 512], 512, False)

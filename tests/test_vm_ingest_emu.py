@@ -31,7 +31,31 @@ def _g1_cases():
             break
     items.append((x + (1 << 383)).to_bytes(48, "big"))  # on curve, outside the subgroup
     items.append((x + (1 << 383) + (1 << 381)).to_bytes(48, "big"))
+    items += _g1_noncanonical(g1c)
     return items
+
+
+def _g1_noncanonical(g1c):
+    """Encodings the reference accepts although they are not canonical (index.ts:304-314): an x coordinate >= p in the
+    381 value bits (`new Fp` reduces it), a missing compression bit (never looked at), an infinity flag with a
+    non-zero body (returns ZERO before the body is read)."""
+    out = []
+    found = 0
+    for i in range(1, 1000):
+        raw = g1c[48 * i: 48 * i + 48]
+        v = int.from_bytes(raw, "big")
+        x = v % (1 << 381)
+        if x + O.P < (1 << 381):
+            out.append((v + O.P).to_bytes(48, "big"))              # x + p, same flags
+            found += 1
+            if found == 3:
+                break
+    assert found == 3
+    v = int.from_bytes(g1c[48 * 7: 48 * 8], "big")
+    out.append((v - (1 << 383)).to_bytes(48, "big"))                # compression bit cleared
+    out.append((v | (1 << 382)).to_bytes(48, "big"))                # infinity flag + the body of 7*G
+    out.append(((1 << 383) | (1 << 382) | (1 << 381) | 12345).to_bytes(48, "big"))  # infinity flag, sign flag, junk
+    return out
 
 
 def g1_expected(item):
@@ -63,7 +87,34 @@ def _g2_cases():
             break
     items.append((xx[1] + (1 << 383)).to_bytes(48, "big") + xx[0].to_bytes(48, "big"))
     items.append((xx[1] + (1 << 383) + (1 << 381)).to_bytes(48, "big") + xx[0].to_bytes(48, "big"))
+    items += _g2_noncanonical(g2c)
     return items
+
+
+def _g2_noncanonical(g2c):
+    """Non-canonical signatures the reference accepts (index.ts:506-514): z2 >= p (48 full bytes, reduced by `new Fp`),
+    z1 mod 2^381 >= p, a missing compression bit, an infinity flag with a non-zero body."""
+    out = []
+    for i in (3, 11):
+        raw = g2c[96 * i: 96 * i + 96]
+        z1, z2 = int.from_bytes(raw[:48], "big"), int.from_bytes(raw[48:], "big")
+        out.append(z1.to_bytes(48, "big") + (z2 + O.P).to_bytes(48, "big"))          # real part + p
+        out.append(z1.to_bytes(48, "big") + (z2 + 2 * O.P).to_bytes(48, "big"))      # real part + 2p (< 2^384)
+    found = 0
+    for i in range(1, 1000):
+        raw = g2c[96 * i: 96 * i + 96]
+        z1 = int.from_bytes(raw[:48], "big")
+        if z1 % (1 << 381) + O.P < (1 << 381):
+            out.append((z1 + O.P).to_bytes(48, "big") + raw[48:])                    # imaginary part + p, same flags
+            found += 1
+            if found == 2:
+                break
+    assert found == 2
+    raw = g2c[96 * 5: 96 * 6]
+    z1 = int.from_bytes(raw[:48], "big")
+    out.append((z1 - (1 << 383)).to_bytes(48, "big") + raw[48:])                     # compression bit cleared
+    out.append((z1 | (1 << 382)).to_bytes(48, "big") + raw[48:])                     # infinity flag + body
+    return out
 
 
 def g2_expected(item):
