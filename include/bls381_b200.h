@@ -94,12 +94,29 @@ int bls381_g1_decompress_batch(const uint8_t* in48, size_t n, uint8_t* out96, in
 /* PointG2.fromSignature for 96-byte compressed signatures incl. assertValidity  replaces index.ts:500-530, 633-638
  *   out192: affine x.c0 || x.c1 || y.c0 || y.c1; status: OK / INFINITY / NO_SQRT / NOT_IN_SUBGROUP       */
 int bls381_g2_decompress_batch(const uint8_t* in96, size_t n, uint8_t* out192, int32_t* status);
+/* PointG1#toHex / toRawBytes (index.ts:355-381) and PointG2#toHex / toSignature (index.ts:586-631) for affine points in
+ * the C-ABI layout; the affine image (0, 0) of ZERO encodes the point at infinity (0xc0 / 0x40 flag byte).
+ *   G1: compressed 48 B (flag bits: 0x80 compressed, 0x20 = (y * 2) / P), uncompressed 96 B = x || y.
+ *   G2: compressed 96 B = x.c1 (+ flags; sign from y.c1, or y.c0 when y.c1 = 0) || x.c0; uncompressed 192 B = x.c1 x.c0 y.c1 y.c0 */
+int bls381_g1_encode_batch(const uint8_t* g1_affine, size_t n, int compressed, uint8_t* out);
+int bls381_g2_encode_batch(const uint8_t* g2_affine, size_t n, int compressed, uint8_t* out);
+/* PointG1.fromHex for 96-byte and PointG2.fromHex for 192-byte UNCOMPRESSED encodings incl. assertValidity
+ *                                                                            replaces index.ts:315-325, 533-538, 565-579
+ *   out: canonical affine coordinates in the C-ABI layout; status: OK / INFINITY (flag 0x40) / NOT_ON_CURVE /
+ *   NOT_IN_SUBGROUP / BAD_ENCODING (G2: 'Invalid encoding flag', or the compression bit set on a 192-byte input)      */
+int bls381_g1_from_uncompressed_batch(const uint8_t* in96, size_t n, uint8_t* out96, int32_t* status);
+int bls381_g2_from_uncompressed_batch(const uint8_t* in192, size_t n, uint8_t* out192, int32_t* status);
 /* PointG2.hashToCurve(msg, {DST})                                              replaces index.ts:481-490
  * (expand_message_xmd index.ts:207-231, hash_to_field :240-267, SWU math.ts:1220-1267, 3-isogeny
  *  math.ts:1315-1325, clearCofactor index.ts:659-672).  msgs: packed bytes, msg_off[n+1] byte offsets.
  *   out192: affine H(m_i).                                                                             */
 int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst,
                             size_t dst_len, uint8_t* out192);
+/* PointG1.hashToCurve(msg, {DST}) (min-signature deployments)                   replaces index.ts:331-339
+ * (hash_to_field with m = 1, map_to_curve_simple_swu_3mod4 math.ts:1270-1313, the 11-isogeny math.ts:1327 + 1612-1790,
+ *  clearCofactor index.ts:401-405).   out96: affine H(m_i).                                                        */
+int bls381_hash_to_g1_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst, size_t dst_len,
+                            uint8_t* out96);
 /* verifyBatch(signature, messages, publicKeys) for byte inputs                  replaces index.ts:792-821
  *   sig96: aggregated signature; pks48: n compressed public keys; status: n + 1 codes (public keys, then signature).
  *   *verdict: 1 true, 0 false, -1 = the reference would throw (a decoding / validity error, see status).   */

@@ -40,6 +40,7 @@ def _load():
     lib.bls381_g1_decompress_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_g2_decompress_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_hash_to_g2_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_hash_to_g1_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_sign_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.bls381_aggregate_g1.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_aggregate_g2.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
@@ -49,6 +50,10 @@ def _load():
     lib.bls381_g1_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_g2_scalar_mul_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_get_public_key_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.bls381_g1_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    lib.bls381_g2_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    lib.bls381_g1_from_uncompressed_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bls381_g2_from_uncompressed_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_verify_batch_partial_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_fp12_product_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     lib.bls381_init_devices.argtypes = [ctypes.c_uint32, ctypes.c_char_p]
@@ -68,6 +73,7 @@ EXPORTS = [
     "bls381_g1_decompress_batch", "bls381_g2_decompress_batch", "bls381_hash_to_g2_batch", "bls381_verify_batch",
     "bls381_sign_batch", "bls381_aggregate_g1", "bls381_aggregate_g2", "bls381_fp12_product",
     "bls381_g1_validate_batch", "bls381_g2_validate_batch", "bls381_g2_scalar_mul_batch", "bls381_g1_scalar_mul_batch", "bls381_verify_batch_partial",
+    "bls381_hash_to_g1_batch", "bls381_g1_encode_batch", "bls381_g2_encode_batch", "bls381_g1_from_uncompressed_batch", "bls381_g2_from_uncompressed_batch",
     "bls381_get_public_key_batch", "bls381_verify_batch_partial_dev", "bls381_fp12_product_dev", "bls381_init_devices",
     "bls381_device_count", "bls381_multi_transport", "bls381_verify_batch_multi",
 ]
@@ -134,6 +140,12 @@ class Engine:
         self._check(self.lib.bls381_hash_to_g2_batch(packed, off, len(msgs), dst, len(dst), out))
         return out.raw
 
+    def hash_to_g1_batch(self, msgs, dst: bytes) -> bytes:
+        packed, off = self._pack(msgs)
+        out = ctypes.create_string_buffer(96 * len(msgs))
+        self._check(self.lib.bls381_hash_to_g1_batch(packed, off, len(msgs), dst, len(dst), out))
+        return out.raw
+
     def verify_batch(self, sig96: bytes, msgs, pks48: bytes, dst: bytes):
         """-> (verdict in {1, 0, -1}, status list of n + 1 codes)"""
         n = len(msgs)
@@ -161,6 +173,28 @@ class Engine:
         out = ctypes.create_string_buffer(96 * n)
         self._check(self.lib.bls381_sign_batch(sks32, packed, off, n, dst, len(dst), out))
         return out.raw
+
+    def g1_encode_batch(self, g1: bytes, n: int, compressed: bool) -> bytes:
+        out = ctypes.create_string_buffer((48 if compressed else 96) * n)
+        self._check(self.lib.bls381_g1_encode_batch(g1, n, int(compressed), out))
+        return out.raw
+
+    def g2_encode_batch(self, g2: bytes, n: int, compressed: bool) -> bytes:
+        out = ctypes.create_string_buffer((96 if compressed else 192) * n)
+        self._check(self.lib.bls381_g2_encode_batch(g2, n, int(compressed), out))
+        return out.raw
+
+    def g1_from_uncompressed_batch(self, in96: bytes, n: int):
+        out = ctypes.create_string_buffer(96 * n)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g1_from_uncompressed_batch(in96, n, out, st))
+        return out.raw, list(st)
+
+    def g2_from_uncompressed_batch(self, in192: bytes, n: int):
+        out = ctypes.create_string_buffer(192 * n)
+        st = (ctypes.c_int32 * n)()
+        self._check(self.lib.bls381_g2_from_uncompressed_batch(in192, n, out, st))
+        return out.raw, list(st)
 
     def get_public_key_batch(self, sks32: bytes) -> bytes:
         """getPublicKey for n 32-byte big-endian scalars -> n x 48 B compressed public keys"""

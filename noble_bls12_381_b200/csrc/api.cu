@@ -59,6 +59,7 @@ struct State {
     // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
     // verifyBatch at 131072 signatures on a B200: 1.26 / 1.39 / 1.42 / 1.40 M sigs/s for 1 / 2 / 3 / 4
     int pairs_per_lane = 3;
+    int log_launches = 0;  // env BLS381_B200_LOG_LAUNCHES: one stderr line per tower-VM launch
 };
 
 // One context per device.  Context 0 is the device of bls381_init(); bls381_init_devices() adds one context per further
@@ -240,6 +241,9 @@ int vm_run(const char* name, uint8_t* const* bufs, const uint32_t* strides, int 
         CUDA_TRY(cudaMemsetAsync(L.ticket, 0, 4, s));
     }
     g.launches.fetch_add(1);
+    if (g.log_launches)  // profiling aid: the i-th vm_kernel launch of an ncu report is the i-th line of this log
+        fprintf(stderr, "[vm_run] %s n=%zu grid=%d warps=%u ctas_per_sm=%d nrec=%u slots=%u far=%u\n", name, n, grid, p->warps, ctas_per_sm, p->nrec,
+                p->nslots, p->nfar);
     rc = BLS381_EPROGRAM;
     if (p->warps == 2) rc = launch_w<2, 8>(L, p->mac2, grid, smem, s);
     if (p->warps == 4) rc = launch_w<4, 4>(L, p->mac2, grid, smem, s);
@@ -418,10 +422,10 @@ int check_offsets(const uint64_t* off, size_t n) {
 
 // ---- ingest: decompression, hash-to-curve, verifyBatch ------------------------------------------------
 __global__ void xmd_kernel(const uint8_t* msgs, const uint64_t* off, size_t n, const uint8_t* dst_prime,
-                           uint32_t dst_prime_len, uint8_t* out) {
+                           uint32_t dst_prime_len, uint8_t* out, uint32_t len_in_bytes = 256) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    sha::expand_xmd_256(msgs + off[i], off[i + 1] - off[i], dst_prime, dst_prime_len, out + 256 * i);
+    sha::expand_xmd(msgs + off[i], off[i + 1] - off[i], dst_prime, dst_prime_len, out + (size_t)len_in_bytes * i, len_in_bytes);
 }
 
 // DST' = DST || len(DST)  (oversize DSTs are hashed first, index.ts:214)
@@ -571,6 +575,7 @@ int init_context(int device, const char* program_dir) {   // caller holds g.mu; 
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
     if (const char* e = getenv("BLS381_B200_PAIRS_PER_LANE")) g.pairs_per_lane = atoi(e);
     if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
+    if (const char* e = getenv("BLS381_B200_LOG_LAUNCHES")) g.log_launches = atoi(e);
     CUDA_TRY(cudaMalloc(&g.d_clk, 16 + 4 * State::kTickets));  // {cycles, ns} clock probe + batch ticket counters
     CUDA_TRY(cudaMemset(g.d_clk, 0, 16 + 4 * State::kTickets));
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
@@ -903,6 +908,40 @@ int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t
     if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, g.d_stage[2], g.stream))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return BLS381_OK;
+}
+
+// PointG1.hashToCurve(msg, {DST})                                              replaces index.ts:331-339
+// (hash_to_field with m = 1: 128 uniform bytes; map_to_curve_simple_swu_3mod4 math.ts:1270-1313; 11-isogeny math.ts:1327,
+//  1612-1790; clearCofactor index.ts:401-405).  out96: affine H(m_i).
+int bls381_hash_to_g1_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t n, const uint8_t* dst, size_t dst_len,
+                            uint8_t* out96) {
+    Enter enter_;
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!msg_off || !dst || !out96) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    int rc;
+    if ((rc = check_offsets(msg_off, n))) return rc;
+    const size_t mbytes = msg_off[n];
+    if (!msgs && mbytes) return fail(BLS381_EINVAL, "null message buffer");
+    if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(2, n * 96)) || (rc = stage(4, n * 128)) || (rc = stage(5, 512))) return rc;
+    cudaStream_t s = g.stream;
+    std::vector<uint8_t> dp;
+    make_dst_prime(dst, dst_len, dp);
+    if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[5], dp.data(), dp.size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(g.ev0, s));
+    xmd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, g.d_stage[5], (uint32_t)dp.size(),
+                                                       g.d_stage[4], 128u);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = run3("hash_to_g1", g.d_stage[4], 128, g.d_stage[2], 96, nullptr, n, s))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(out96, g.d_stage[2], n * 96, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
     return BLS381_OK;
 }
 
@@ -1386,6 +1425,129 @@ int bls381_fp12_product(const uint8_t* in_fp12, size_t n, int with_final_exp, ui
     CUDA_TRY(cudaMemcpyAsync(out_fp12, res, 576, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return BLS381_OK;
+}
+
+// ---- wire formats (index.ts:298-381, 532-631) on the device -----------------------------------------------------
+// y > (p - 1) / 2 for a 48-byte big-endian canonical value: the reference's `(y * 2) / P` flag
+__device__ __forceinline__ int be48_gt_half(const uint8_t* y) {
+    static const uint8_t half[48] = {
+        0x0d, 0x00, 0x88, 0xf5, 0x1c, 0xbf, 0xf3, 0x4d, 0x25, 0x8d, 0xd3, 0xdb, 0x21, 0xa5, 0xd6, 0x6b, 0xb2, 0x3b, 0xa5, 0xc2, 0x79, 0xc2, 0x89, 0x5f,
+        0xb3, 0x98, 0x69, 0x50, 0x7b, 0x58, 0x7b, 0x12, 0x0f, 0x55, 0xff, 0xff, 0x58, 0xa9, 0xff, 0xff, 0xdc, 0xff, 0x7f, 0xff, 0xff, 0xff, 0xd5, 0x55};
+    int gt = 0, decided = 0;
+    for (int k = 0; k < 48; ++k) {
+        const int a = y[k], h = half[k];
+        gt |= (!decided) & (a > h);
+        decided |= (a != h);
+    }
+    return gt;
+}
+__device__ __forceinline__ int be_is_zero(const uint8_t* p, int n) {
+    int any = 0;
+    for (int k = 0; k < n; ++k) any |= p[k];
+    return any == 0;
+}
+
+// PointG1#toHex (index.ts:359-381) / PointG2#toHex (index.ts:604-631) from affine C-ABI coordinates; the affine image (0, 0)
+// of ZERO (math.ts:955) encodes the point at infinity.  g2 = 0: in 96 B -> out 48 / 96 B; g2 = 1: in 192 B -> out 96 / 192 B
+__global__ void encode_points_kernel(const uint8_t* in, uint8_t* out, size_t n, int g2, int compressed) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int fe = 48, inb = g2 ? 192 : 96;
+    const int outb = g2 ? (compressed ? 96 : 192) : (compressed ? 48 : 96);
+    const uint8_t* a = in + (size_t)inb * i;
+    uint8_t* o = out + (size_t)outb * i;
+    if (be_is_zero(a, inb)) {
+        for (int k = 0; k < outb; ++k) o[k] = 0;
+        o[0] = compressed ? 0xC0 : 0x40;
+        return;
+    }
+    if (!g2) {
+        for (int k = 0; k < (compressed ? fe : 2 * fe); ++k) o[k] = a[k];
+        if (compressed) o[0] |= (uint8_t)(0x80 | (be48_gt_half(a + fe) << 5));
+        return;
+    }
+    // C-ABI order x.c0 x.c1 y.c0 y.c1 ; wire order x.c1 x.c0 [y.c1 y.c0]
+    const uint8_t *x0 = a, *x1 = a + fe, *y0 = a + 2 * fe, *y1 = a + 3 * fe;
+    for (int k = 0; k < fe; ++k) { o[k] = x1[k]; o[fe + k] = x0[k]; }
+    if (compressed) {
+        const int flag = be_is_zero(y1, fe) ? be48_gt_half(y0) : be48_gt_half(y1);
+        o[0] |= (uint8_t)(0x80 | (flag << 5));
+    } else {
+        for (int k = 0; k < fe; ++k) { o[2 * fe + k] = y1[k]; o[3 * fe + k] = y0[k]; }
+    }
+}
+
+// flag byte of an uncompressed encoding (index.ts:317, 533-538, 565-568): overrides the status of the validity program
+__global__ void uncompressed_flags_kernel(const uint8_t* in, int32_t* status, uint8_t* out, size_t n, int g2) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int inb = g2 ? 192 : 96;
+    const uint8_t b0 = in[(size_t)inb * i];
+    int32_t v = status[i];
+    if (g2) {
+        const uint8_t m = b0 & 0xE0;
+        if (m == 0x20 || m == 0x60 || m == 0xE0 || (m & 0x80)) v = BLS381_ST_BAD_ENCODING;  // 'Invalid encoding flag' / not the uncompressed form
+        else if (b0 & 0x40) v = BLS381_ST_INFINITY;
+    } else if (b0 & 0x40) {
+        v = BLS381_ST_INFINITY;
+    }
+    status[i] = v;
+    if (v == BLS381_ST_INFINITY || v == BLS381_ST_BAD_ENCODING)
+        for (int k = 0; k < inb; ++k) out[(size_t)inb * i + k] = 0;
+}
+
+static int encode_host(bool g2, const uint8_t* in, size_t n, int compressed, uint8_t* out) {
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in || !out) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    const size_t inb = g2 ? 192 : 96, outb = g2 ? (compressed ? 96 : 192) : (compressed ? 48 : 96);
+    int rc;
+    if ((rc = stage(0, n * inb)) || (rc = stage(2, n * outb))) return rc;
+    cudaStream_t s = g.stream;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * inb, cudaMemcpyHostToDevice, s));
+    encode_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[0], g.d_stage[2], n, g2 ? 1 : 0, compressed ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[2], n * outb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return BLS381_OK;
+}
+
+int bls381_g1_encode_batch(const uint8_t* g1_affine, size_t n, int compressed, uint8_t* out) {
+    Enter enter_;
+    return encode_host(false, g1_affine, n, compressed, out);
+}
+
+int bls381_g2_encode_batch(const uint8_t* g2_affine, size_t n, int compressed, uint8_t* out) {
+    Enter enter_;
+    return encode_host(true, g2_affine, n, compressed, out);
+}
+
+static int from_uncompressed_host(bool g2, const uint8_t* in, size_t n, uint8_t* out, int32_t* status) {
+    if (!g.inited) return fail(BLS381_ENOINIT, "bls381_init() has not been called");
+    if (!in || !out || !status) return fail(BLS381_EINVAL, "null argument");
+    if (n == 0) return BLS381_OK;
+    const uint32_t ab = g2 ? 192 : 96;
+    int rc;
+    if ((rc = stage(0, n * ab)) || (rc = stage(2, n * ab)) || (rc = stage(6, n * 4))) return rc;
+    cudaStream_t s = g.stream;
+    CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * ab, cudaMemcpyHostToDevice, s));
+    if ((rc = run3(g2 ? "g2_from_uncompressed" : "g1_from_uncompressed", g.d_stage[0], ab, g.d_stage[2], ab, (int32_t*)g.d_stage[6], n, s))) return rc;
+    uncompressed_flags_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[0], (int32_t*)g.d_stage[6], g.d_stage[2], n, g2 ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[2], n * ab, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return BLS381_OK;
+}
+
+int bls381_g1_from_uncompressed_batch(const uint8_t* in96, size_t n, uint8_t* out96, int32_t* status) {
+    Enter enter_;
+    return from_uncompressed_host(false, in96, n, out96, status);
+}
+
+int bls381_g2_from_uncompressed_batch(const uint8_t* in192, size_t n, uint8_t* out192, int32_t* status) {
+    Enter enter_;
+    return from_uncompressed_host(true, in192, n, out192, status);
 }
 
 static int validate_host(bool g2, const uint8_t* in, size_t n, int32_t* status) {

@@ -79,15 +79,17 @@ SHA_HD void final(Ctx& c, uint8_t* out) {
     }
 }
 
-// uniform = expand_message_xmd(msg, DST, 256); dst_prime = DST || I2OSP(len(DST), 1) (already shortened)
-SHA_HD void expand_xmd_256(const uint8_t* msg, uint64_t msg_len, const uint8_t* dst_prime, uint32_t dst_prime_len, uint8_t* out256) {
+// uniform = expand_message_xmd(msg, DST, len_in_bytes) (index.ts:207-231), len_in_bytes a multiple of 32 up to 256: 256 for
+// hash_to_field of G2 (count 2, m 2, L 64), 128 for G1 (count 2, m 1); dst_prime = DST || I2OSP(len(DST), 1) (already shortened)
+SHA_HD void expand_xmd(const uint8_t* msg, uint64_t msg_len, const uint8_t* dst_prime, uint32_t dst_prime_len, uint8_t* out256,
+                       uint32_t len_in_bytes = 256) {
     Ctx c;
     uint8_t b0[32], bi[32], tmp[32];
     init(c);
     uint8_t z = 0;
     for (int i = 0; i < 64; ++i) update(c, &z, 1);  // Z_pad
     update(c, msg, msg_len);
-    const uint8_t lib[3] = {0x01, 0x00, 0x00};      // I2OSP(256, 2) || I2OSP(0, 1)
+    const uint8_t lib[3] = {(uint8_t)(len_in_bytes >> 8), (uint8_t)len_in_bytes, 0x00};  // I2OSP(len_in_bytes, 2) || I2OSP(0, 1)
     update(c, lib, 3);
     update(c, dst_prime, dst_prime_len);
     final(c, b0);
@@ -98,7 +100,7 @@ SHA_HD void expand_xmd_256(const uint8_t* msg, uint64_t msg_len, const uint8_t* 
     update(c, dst_prime, dst_prime_len);
     final(c, bi);
     for (int k = 0; k < 32; ++k) out256[k] = bi[k];
-    for (int i = 2; i <= 8; ++i) {
+    for (int i = 2; i <= (int)(len_in_bytes / 32); ++i) {
         for (int k = 0; k < 32; ++k) tmp[k] = b0[k] ^ bi[k];
         init(c);
         update(c, tmp, 32);

@@ -734,6 +734,123 @@ def build_hash_to_g2(warps=8) -> Builder:
 PROGRAMS["hash_to_g2"] = build_hash_to_g2
 
 
+# ------------------------------------------------------------------------------------------ hash to G1
+# (min-signature deployments hash to G1)
+_SWU1_A = 0x144698A3B8E9433D693A02C96D4982B0EA985383EE66A8D8E8981AEFD881AC98936F8DA0E0F97F5CF428082D584C1D  # math.ts:1271-1273
+_SWU1_B = 0x12E2908D11688030018B12E8753EEE3B2016C1F0F24F4070A0B9C14FCEF35EF55A23215A316CEAA5D1CC48E98E172BE0  # math.ts:1274-1276
+_SWU1_Z = 11
+
+
+def _swu_g1(ig: Ingest, u: Lin):
+    """map_to_curve_simple_swu_3mod4 (math.ts:1270-1313), branch-free, returning the point of E' as (xNum : y * xDen : xDen)."""
+    b, t = ig.b, ig.t
+    m = lambda q: Lin.of(b.mat(q))
+    A, B, Z = t.fp_const(_SWU1_A), t.fp_const(_SWU1_B), t.fp_const(_SWU1_Z)
+    c2 = t.fp_const(pow(pow((-_SWU1_Z) % P, 3, P), (P + 1) // 4, P))  # sqrt((-Z)^3)
+    assert pow(pow(pow((-_SWU1_Z) % P, 3, P), (P + 1) // 4, P), 2, P) == pow((-_SWU1_Z) % P, 3, P)
+    u = m(u)
+    tv1 = m(u * u)
+    tv3 = m(tv1 * Z)
+    xd0 = m(tv3 * tv3 + tv3)
+    xn1 = m((xd0 + t.fp_const(1)) * B)
+    xn2 = m(tv3 * xn1)
+    xd = m((-xd0) * A)
+    xd = Lin.of(b.select(b.is_zero(xd), m(t.fp_const(_SWU1_A * _SWU1_Z % P)), xd))
+    tv2 = m(xd * xd)
+    gxd = m(tv2 * xd)
+    atv2 = m(tv2 * A)
+    gx1 = m(m(xn1 * xn1 + atv2) * xn1 + gxd * B)
+    tv2 = m(gx1 * gxd)
+    tv4 = m(m(gxd * gxd) * tv2)
+    y1 = m(pow_fixed(lambda x, y: x * y, lambda x: x * x, m, t.fp_const(1), tv4, (P - 3) // 4) * tv2)
+    y2 = m(m(m(y1 * c2) * tv1) * u)
+    ok = b.is_zero(m(y1 * y1) * gxd - gx1)
+    xnum = Lin.of(b.select(ok, xn1, xn2))
+    ypos = Lin.of(b.select(ok, y1, y2))
+    flip = b.flag_xor(b.parity(u), b.parity(ypos))  # sgn0_m_eq_1(u) != sgn0_m_eq_1(yPos)
+    y = Lin.of(b.select(flip, -ypos, ypos))
+    return (xnum, m(y * xd), xd)
+
+
+def _add_generic_fp(ig: Ingest, p, q):
+    """add-1998-cmo-2 as coded in math.ts:1008-1024 over Fp (valid on the isogenous curve E', a != 0; the special cases
+    P == +-Q cannot be reached by two independent SWU outputs in practice)."""
+    b = ig.b
+    m = lambda e: Lin.of(b.mat(e))
+    X1, Y1, Z1 = p
+    X2, Y2, Z2 = q
+    U2 = m(Y1 * Z2)
+    V2 = m(X1 * Z2)
+    U = m(Y2 * Z1 - U2)
+    V = m(X2 * Z1 - V2)
+    VV = m(V * V)
+    VVV = m(VV * V)
+    V2VV = m(V2 * VV)
+    W = m(Z1 * Z2)
+    Av = m(m(U * U) * W - VVV - V2VV * 2)
+    return (m(V * Av), m(U * (V2VV - Av) - VVV * U2), m(VVV * W))
+
+
+def _isogeny11_projective(ig: Ingest, p):
+    """isogenyMapG1 (math.ts:1306-1313, 1327; coefficients math.ts:1612-1790) on a projective point of E', staying projective:
+    x' = N_x / (Z D_x), y' = Y N_y / (Z D_y) with the polynomials homogenised -> (N_x D_y : Y N_y D_x : Z D_x D_y)."""
+    from . import iso11
+    b, t = ig.b, ig.t
+    m = lambda e: Lin.of(b.mat(e))
+    X, Y, Z = p
+    xp, zp = [None, X], [None, Z]
+    for k in range(2, 16):
+        xp.append(m(xp[k // 2] * xp[k - k // 2]))
+        zp.append(m(zp[k // 2] * zp[k - k // 2]))
+
+    def mono(i, deg):  # X^i Z^(deg - i)
+        j = deg - i
+        if i == 0:
+            return zp[j]
+        if j == 0:
+            return xp[i]
+        return m(xp[i] * zp[j])
+
+    def poly(coeffs):  # highest degree first (Horner order of the reference)
+        deg = len(coeffs) - 1
+        acc = None
+        for k, c in enumerate(coeffs):
+            if c % P == 0:
+                continue
+            term = mono(deg - k, deg) * t.fp_const(c)
+            acc = term if acc is None else acc + term
+        return m(acc)
+
+    NX, DX, NY, DY = poly(iso11.XNUM), poly(iso11.XDEN), poly(iso11.YNUM), poly(iso11.YDEN)
+    ZDX = m(Z * DX)
+    return (m(NX * DY), m(m(Y * NY) * DX), m(ZDX * DY))
+
+
+def build_hash_to_g1(warps=4) -> Builder:
+    """PointG1.hashToCurve (index.ts:331-339) from the 128 uniform bytes of expand_message_xmd (hash_to_field, m = 1):
+    buffer 0: n x 128 B -> buffer 2: n x 96 B affine H(m)."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    two256 = t.fp_const(1 << 256)
+    us = []
+    for j in range(2):
+        hi = Lin.of(b.inp_bytes(BUF_IN, 64 * j, 32))
+        lo = Lin.of(b.inp_bytes(BUF_IN, 64 * j + 32, 32))
+        us.append(Lin.of(b.mat(hi * two256 + lo)))
+    s = _add_generic_fp(ig, _swu_g1(ig, us[0]), _swu_g1(ig, us[1]))
+    e = _isogeny11_projective(ig, s)
+    G = ig.G1
+    h = G.add(G.mul_fixed(e, X_PARAM), e)  # clearCofactor (index.ts:401-405): [|x|]P + P
+    x, y = ig.g1_to_affine(h)
+    b.out(x, BUF_OUT, 0)
+    b.out(y, BUF_OUT, 1)
+    return b
+
+
+PROGRAMS["hash_to_g1"] = build_hash_to_g1
+
+
 # ------------------------------------------------------------------------------------------ sign / aggregate
 BUF_AUX = 1  # second input buffer (scalars for `sign`, status words for the sums)
 
@@ -892,6 +1009,36 @@ def _build_validate(which: str, warps: int) -> Builder:
     return b
 
 
+def _build_from_uncompressed(which: str, warps: int) -> Builder:
+    """PointG1.fromHex for 96-byte / PointG2.fromHex for 192-byte UNCOMPRESSED input (index.ts:315-325, 565-579): the
+    coordinates are taken as they are (no flag bits are cleared, `new Fp` reduces them mod p), then assertValidity.
+    buffer 0: the wire bytes (G1: x || y; G2: x.c1 || x.c0 || y.c1 || y.c0); buffer 2: canonical affine coordinates in the
+    C-ABI order (G2: x.c0, x.c1, y.c0, y.c1); buffer 5: status.  The infinity / encoding flags of byte 0 are handled by the
+    caller (api.cu: a byte-level kernel), which overrides the status word."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    one = Lin.of(b.mat(t.fp_const(1)))
+    if which == "g1":
+        x, y = Lin.of(b.inp(BUF_IN, 0)), Lin.of(b.inp(BUF_IN, 1))
+        p = (x, y, one)
+        G, tors = ig.G1, ig.g1_is_torsion_free
+        outs = [x, y]
+    else:
+        x1, x0, y1, y0 = (Lin.of(b.inp(BUF_IN, k)) for k in range(4))
+        z = E2(one, Lin.of(b.mat(Lin.of(b.const_raw(0)))))
+        p = (E2(x0, x1), E2(y0, y1), z)
+        G, tors = ig.G2, ig.g2_is_torsion_free
+        outs = [x0, x1, y0, y1]
+    not_on = b.flag_not(G.is_on_curve(p))
+    not_sub = b.flag_not(tors(p))
+    st = ig.status_chain([(not_on, ST_NOT_ON_CURVE), (not_sub, ST_NOT_IN_SUBGROUP)])
+    for k, v in enumerate(outs):
+        b.out(v, BUF_OUT, k)
+    b.out_word(st, BUF_STATUS)
+    return b
+
+
 def build_g2_scalar_mul(warps=4) -> Builder:
     """ProjectivePoint#multiply(scalar) on G2 (math.ts:1061-1078): buffer 0 affine point, buffer 1 32-byte scalar
     (0 < k <= r) -> buffer 2 affine result, buffer 5 flag word (bit1 = result is the point at infinity)."""
@@ -930,6 +1077,8 @@ def build_g1_scalar_mul(warps=4) -> Builder:
 
 
 PROGRAMS.update({
+    "g1_from_uncompressed": lambda w: _build_from_uncompressed("g1", w),
+    "g2_from_uncompressed": lambda w: _build_from_uncompressed("g2", w),
     "g1_scalar_mul": build_g1_scalar_mul,
     "g1_validate": lambda w: _build_validate("g1", w),
     "g2_validate": lambda w: _build_validate("g2", w),

@@ -1098,6 +1098,76 @@ def g2_hash_to_curve(msg: bytes, dst: bytes = DEFAULT_DST):  # index.ts:481-490
     return g2_clear_cofactor((x3, y3, FP2_ONE))
 
 
+# ----------------------------------------------------------------------------- hash to curve G1 (math.ts:1270-1313, 1612-1790)
+from .iso11_table import ISO11_XNUM, ISO11_XDEN, ISO11_YNUM, ISO11_YDEN  # noqa: E402
+
+_SWU_G1_A = 0x144698A3B8E9433D693A02C96D4982B0EA985383EE66A8D8E8981AEFD881AC98936F8DA0E0F97F5CF428082D584C1D  # math.ts:1271-1273
+_SWU_G1_B = 0x12E2908D11688030018B12E8753EEE3B2016C1F0F24F4070A0B9C14FCEF35EF55A23215A316CEAA5D1CC48E98E172BE0  # math.ts:1274-1276
+_SWU_G1_Z = 11  # math.ts:1277
+
+
+def map_to_curve_simple_swu_3mod4(u: int):  # math.ts:1270-1313
+    A, B, Z = _SWU_G1_A, _SWU_G1_B, _SWU_G1_Z
+    u %= P
+    c1 = (P - 3) // 4
+    c2 = fp_sqrt(pow((-Z) % P, 3, P))  # sqrt((-Z)^3): a static value, the root always exists
+    tv1 = u * u % P
+    tv3 = Z * tv1 % P
+    x_den = (tv3 * tv3 + tv3) % P
+    x_num1 = (x_den + 1) * B % P
+    x_num2 = tv3 * x_num1 % P
+    x_den = (-A) * x_den % P
+    if x_den == 0:
+        x_den = A * Z % P
+    tv2 = x_den * x_den % P
+    gxd = tv2 * x_den % P
+    tv2 = A * tv2 % P
+    gx1 = (x_num1 * x_num1 + tv2) * x_num1 % P
+    tv2 = B * gxd % P
+    gx1 = (gx1 + tv2) % P
+    tv2 = gx1 * gxd % P
+    tv4 = gxd * gxd % P * tv2 % P
+    y1 = pow(tv4, c1, P) * tv2 % P
+    y2 = y1 * c2 % P * tv1 % P * u % P
+    if y1 * y1 % P * gxd % P == gx1:
+        x_num, y_pos = x_num1, y1
+    else:
+        x_num, y_pos = x_num2, y2
+    y = y_pos if (u % 2) == (y_pos % 2) else (-y_pos) % P  # sgn0_m_eq_1, math.ts:1187-1189
+    return x_num * fp_inv(x_den) % P, y
+
+
+def isogeny_map_g1(x: int, y: int):  # math.ts:1306-1313, 1327 with ISOGENY_COEFFICIENTS_G1
+    def horner(coeffs):
+        acc = coeffs[0]
+        for c in coeffs[1:]:
+            acc = (acc * x + c) % P
+        return acc
+
+    x_num, x_den, y_num, y_den = (horner(c) for c in (ISO11_XNUM, ISO11_XDEN, ISO11_YNUM, ISO11_YDEN))
+    return x_num * fp_inv(x_den) % P, y * (y_num * fp_inv(y_den) % P) % P
+
+
+def g1_clear_cofactor(p):  # index.ts:401-405:  [|x|]P + P
+    return pt_add(G1, pt_multiply_unsafe(G1, p, X_PARAM), p)
+
+
+def g1_hash_to_curve(msg: bytes, dst: bytes = DEFAULT_DST):  # index.ts:331-339
+    (u0,), (u1,) = hash_to_field(msg, 2, dst, m=1)
+    x0, y0 = map_to_curve_simple_swu_3mod4(u0)
+    x1, y1 = map_to_curve_simple_swu_3mod4(u1)
+    x2, y2 = pt_to_affine(G1, pt_add(G1, (x0, y0, 1), (x1, y1, 1)))
+    x3, y3 = isogeny_map_g1(x2, y2)
+    return g1_clear_cofactor((x3, y3, 1))
+
+
+def g1_encode_to_curve(msg: bytes, dst: bytes = DEFAULT_DST):  # index.ts:341-350
+    ((u0,),) = hash_to_field(msg, 1, dst, m=1)
+    x0, y0 = map_to_curve_simple_swu_3mod4(u0)
+    x1, y1 = isogeny_map_g1(x0, y0)
+    return g1_clear_cofactor((x1, y1, 1))
+
+
 def g2_encode_to_curve(msg: bytes, dst: bytes = DEFAULT_DST):  # index.ts:491-497
     u = hash_to_field(msg, 1, dst)
     x0, y0 = map_to_curve_simple_swu_9mod16(u[0])

@@ -109,7 +109,7 @@ def main():
     for p in os.listdir(OUT):
         os.chmod(f"{OUT}/{p}", 0o644)
 
-    # 4. hash-to-curve vectors (G2 + xmd only: G1 hashing is out of scope)
+    # 4. hash-to-curve vectors (xmd, G2, and -- SURVEY section 8f-4 -- the G1 suites)
     src = open(f"{REF}/hashToCurve.test.ts").read()
     long_dst = js_strings(re.search(r"const LONG_DST =(.*?);", src, re.S).group(1))
     h2c = {
@@ -121,6 +121,10 @@ def main():
         "g2_rfc_ro": {"dst": "QUUX-V01-CS02-with-BLS12381G2_XMD:SHA-256_SSWU_RO_", "vectors": parse_vectors(src, "VECTORS_G2_RO")},
         "g2_rfc_nu": {"dst": "QUUX-V01-CS02-with-BLS12381G2_XMD:SHA-256_SSWU_NU_", "vectors": parse_vectors(src, "VECTORS_G2_NU")},
         "g2_kilic_nu": {"dst": "BLS12381G2_XMD:SHA-256_SSWU_NU_TESTGEN", "vectors": parse_vectors(src, "VECTORS_ENCODE_G2")},
+        "g1_kilic_ro": {"dst": "BLS12381G1_XMD:SHA-256_SSWU_RO_TESTGEN", "vectors": parse_vectors(src, "VECTORS_G1")},
+        "g1_rfc_ro": {"dst": "QUUX-V01-CS02-with-BLS12381G1_XMD:SHA-256_SSWU_RO_", "vectors": parse_vectors(src, "VECTORS_G1_RO")},
+        "g1_rfc_nu": {"dst": "QUUX-V01-CS02-with-BLS12381G1_XMD:SHA-256_SSWU_NU_", "vectors": parse_vectors(src, "VECTORS_G1_NU")},
+        "g1_kilic_nu": {"dst": "BLS12381G1_XMD:SHA-256_SSWU_NU_TESTGEN", "vectors": parse_vectors(src, "VECTORS_ENCODE_G1")},
     }
     json.dump(h2c, open(f"{OUT}/hash_to_curve.json", "w"), indent=1)
     print({k: len(v["vectors"]) for k, v in h2c.items() if isinstance(v, dict)})

@@ -208,3 +208,96 @@ def test_random_pairs_config2_sample_vs_c_oracle(eng):
     assert out == C.pairing_batch(g1, g2, n, True)
     raw = eng.pairing_batch(g1[: 96 * 512], g2[: 192 * 512], 512, False)
     assert raw == C.pairing_batch(g1[: 96 * 512], g2[: 192 * 512], 512, False)
+
+
+# ---- wire formats end to end on the device against ALL 4 x 1000 zkcrypto vectors (test/deterministic.test.ts:49-113) -----
+def _zk(name):
+    return open(os.path.join(GOLDEN, name), "rb").read()
+
+
+def test_zkcrypto_encode_direction_all_4000_vectors(eng):
+    """i * G (i = 0..999) computed on the device and ENCODED on the device: compressed and uncompressed, G1 and G2."""
+    from noble_bls12_381_b200 import synth
+    n = 1000
+    ks = b"".join(i.to_bytes(32, "big") for i in range(1, n))
+    base1 = (synth.GX.to_bytes(48, "big") + synth.GY.to_bytes(48, "big")) * (n - 1)
+    base2 = b"".join(c.to_bytes(48, "big") for c in (synth.G2X[0], synth.G2X[1], synth.G2Y[0], synth.G2Y[1])) * (n - 1)
+    g1, f1 = eng.g1_scalar_mul_batch(base1, ks, n - 1)
+    g2, f2 = eng.g2_scalar_mul_batch(base2, ks, n - 1)
+    assert not any(f1) and not any(f2)
+    g1 = bytes(96) + g1      # entry 0 of every file is the point at infinity: affine image (0, 0)
+    g2 = bytes(192) + g2
+    assert eng.g1_encode_batch(g1, n, True) == _zk("zkcrypto_g1_compressed.dat")
+    assert eng.g1_encode_batch(g1, n, False) == _zk("zkcrypto_g1_uncompressed.dat")
+    assert eng.g2_encode_batch(g2, n, True) == _zk("zkcrypto_g2_compressed.dat")
+    assert eng.g2_encode_batch(g2, n, False) == _zk("zkcrypto_g2_uncompressed.dat")
+    # the same multiples by the other two multipliers the reference's test uses: running sum (aggregate) and getPublicKey
+    assert eng.get_public_key_batch(ks) == _zk("zkcrypto_g1_compressed.dat")[48:]
+
+
+def test_zkcrypto_decode_direction_all_4000_vectors(eng):
+    """All four files DECODED on the device (compressed: PointG1.fromHex / PointG2.fromSignature; uncompressed: the 96 / 192
+    byte branches of fromHex incl. assertValidity), re-encoded, and compared with the device's own multiples."""
+    n = 1000
+    g1c, g1u, g2c, g2u = (_zk("zkcrypto_%s.dat" % k) for k in ("g1_compressed", "g1_uncompressed", "g2_compressed", "g2_uncompressed"))
+    a1, s1 = eng.g1_decompress_batch(g1c, n)
+    b1, t1 = eng.g1_from_uncompressed_batch(g1u, n)
+    a2, s2 = eng.g2_decompress_batch(g2c, n)
+    b2, t2 = eng.g2_from_uncompressed_batch(g2u, n)
+    for st in (s1, t1, s2, t2):
+        assert st[0] == 1 and not any(st[1:])      # entry 0: infinity; the rest valid
+    assert a1[96:] == b1[96:] == g1u[96:]
+    assert a2[192:] == b2[192:]
+    # round trip through the encoders
+    assert b1[:96] == bytes(96) and b2[:192] == bytes(192)      # the decoders hand back the affine image (0, 0) of ZERO
+    e1 = eng.g1_encode_batch(b1, n, True)
+    assert [i for i in range(n) if e1[48 * i: 48 * i + 48] != g1c[48 * i: 48 * i + 48]] == []
+    e2 = eng.g2_encode_batch(b2, n, False)
+    assert [i for i in range(n) if e2[192 * i: 192 * i + 192] != g2u[192 * i: 192 * i + 192]] == []
+    e3 = eng.g2_encode_batch(bytes(192) + a2[192:], n, True)
+    assert [i for i in range(n) if e3[96 * i: 96 * i + 96] != g2c[96 * i: 96 * i + 96]] == []
+
+
+def test_uncompressed_decode_edge_cases_follow_the_reference(eng, O):
+    g1u, g2u = _zk("zkcrypto_g1_uncompressed.dat"), _zk("zkcrypto_g2_uncompressed.dat")
+    # G1 (index.ts:315-325): infinity flag with junk -> ZERO; off curve; coordinates >= p are reduced by `new Fp`
+    p5 = g1u[96 * 5: 96 * 6]
+    x, y = int.from_bytes(p5[:48], "big"), int.from_bytes(p5[48:], "big")
+    items = [p5, bytes([0x40]) + p5[1:], p5[:95] + bytes([p5[95] ^ 1]), (x + O.P).to_bytes(48, "big") + (y + 2 * O.P).to_bytes(48, "big")]
+    xs = 1
+    while True:
+        xs += 1
+        ys = O.fp_sqrt((xs**3 + 4) % O.P)
+        if ys is not None and not O.g1_is_torsion_free((xs, ys, 1)):
+            break
+    items.append(xs.to_bytes(48, "big") + ys.to_bytes(48, "big"))
+    out, st = eng.g1_from_uncompressed_batch(b"".join(items), len(items))
+    assert st == [0, 1, 2, 0, 3]
+    assert out[:96] == p5 and out[96 * 3: 96 * 4] == p5 and out[96: 192] == bytes(96)
+    # G2 (index.ts:533-538, 565-579): invalid flag combinations, compression bit on a 192-byte input, infinity, off curve
+    q7 = g2u[192 * 7: 192 * 8]
+    bad_flag = lambda m: bytes([(q7[0] & 0x1F) | m]) + q7[1:]
+    items = [q7, bad_flag(0x20), bad_flag(0x60), bad_flag(0xE0), bad_flag(0x80), bad_flag(0x40), q7[:191] + bytes([q7[191] ^ 1])]
+    out, st = eng.g2_from_uncompressed_batch(b"".join(items), len(items))
+    assert st == [0, 4, 4, 4, 4, 1, 2]
+    want = q7[48:96] + q7[:48] + q7[144:192] + q7[96:144]      # wire x.c1 x.c0 y.c1 y.c0 -> C-ABI x.c0 x.c1 y.c0 y.c1
+    assert out[:192] == want
+
+
+def test_hash_to_g1_reference_vectors_and_random(eng, O):
+    """bls381_hash_to_g1_batch: test/hashToCurve.test.ts G1 random-oracle suites + random messages / DSTs vs the oracle."""
+    import json
+    d = json.load(open(os.path.join(GOLDEN, "hash_to_curve.json")))
+    for key in ("g1_kilic_ro", "g1_rfc_ro"):
+        dst = d[key]["dst"].encode("latin1")
+        vecs = d[key]["vectors"]
+        out = eng.hash_to_g1_batch([v["msg"].encode("latin1") for v in vecs], dst)
+        for i, v in enumerate(vecs):
+            assert out[96 * i: 96 * i + 96].hex() == v["expected"], (key, i)
+    rng = random.Random(5)
+    msgs = [bytes(rng.randrange(256) for _ in range(rng.randrange(0, 200))) for _ in range(70)]
+    for dst in (DST, b"Q" * 300):
+        out = eng.hash_to_g1_batch(msgs, dst)
+        for i in (0, 1, 31, 32, 69):
+            p = O.pt_to_affine(O.G1, O.g1_hash_to_curve(msgs[i], dst))
+            assert out[96 * i: 96 * i + 96] == p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big"), i

@@ -218,3 +218,20 @@ def test_verify_and_batch_truth_table():
     # infinity pubkey -> pairing throws inside try -> false
     inf = bytes([0xC0]) + bytes(47)
     assert O.verify_batch(agg, msgs, [inf] + pubs[1:]) is False
+
+
+def test_hash_to_curve_g1_vectors():
+    # test/hashToCurve.test.ts:352-530: kilic and RFC suites for PointG1.hashToCurve / encodeToCurve (p.toHex(), uncompressed)
+    d = json.load(open(os.path.join(GOLDEN, "hash_to_curve.json")))
+    for key, fn in (
+        ("g1_kilic_ro", O.g1_hash_to_curve),
+        ("g1_rfc_ro", O.g1_hash_to_curve),
+        ("g1_rfc_nu", O.g1_encode_to_curve),
+        ("g1_kilic_nu", O.g1_encode_to_curve),
+    ):
+        dst = d[key]["dst"].encode("latin1")
+        assert len(d[key]["vectors"]) >= 4
+        for v in d[key]["vectors"]:
+            p = fn(v["msg"].encode("latin1"), dst)
+            assert O.g1_to_hex(p).hex() == v["expected"], key
+            assert O.g1_is_on_curve(p) and O.g1_is_torsion_free(p)

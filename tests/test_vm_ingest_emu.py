@@ -303,3 +303,42 @@ def test_validate_programs_edge_points():
     raw = b"".join(b"".join(v.to_bytes(48, "big") for v in (a[0], a[1], c[0], c[1])) for a, c in pts)
     emu.run_program(b2, {0: (bytearray(raw), 192), 5: (st, 4)}, n)
     assert list(struct.unpack("<%di" % n, st)) == exp
+
+
+def test_from_uncompressed_programs():
+    """index.ts:315-325 / 565-579 on the emulator: coordinates as they are (reduced mod p), on-curve and subgroup checks."""
+    g1u = open(os.path.join(GOLDEN, "zkcrypto_g1_uncompressed.dat"), "rb").read()
+    g2u = open(os.path.join(GOLDEN, "zkcrypto_g2_uncompressed.dat"), "rb").read()
+    p5 = g1u[96 * 5: 96 * 6]
+    x, y = int.from_bytes(p5[:48], "big"), int.from_bytes(p5[48:], "big")
+    items = [p5, g1u[96 * 999: 96 * 1000], p5[:95] + bytes([p5[95] ^ 1]), (x + O.P).to_bytes(48, "big") + (y + 2 * O.P).to_bytes(48, "big")]
+    n = len(items)
+    b = vmcompile.compile_program("g1_from_uncompressed")
+    out, st = bytearray(96 * n), bytearray(4 * n)
+    emu.run_program(b, {0: (bytearray(b"".join(items)), 96), 2: (out, 96), 5: (st, 4)}, n)
+    assert list(struct.unpack("<%di" % n, st)) == [0, 0, curves.ST_NOT_ON_CURVE, 0]
+    assert bytes(out[:96]) == p5 and bytes(out[96 * 3:]) == p5 and bytes(out[96:192]) == items[1]
+    q = g2u[192 * 7: 192 * 8]
+    items = [q, g2u[192 * 500: 192 * 501], q[:191] + bytes([q[191] ^ 1])]
+    n = len(items)
+    b = vmcompile.compile_program("g2_from_uncompressed")
+    out, st = bytearray(192 * n), bytearray(4 * n)
+    emu.run_program(b, {0: (bytearray(b"".join(items)), 192), 2: (out, 192), 5: (st, 4)}, n)
+    assert list(struct.unpack("<%di" % n, st)) == [0, 0, curves.ST_NOT_ON_CURVE]
+    assert bytes(out[:192]) == q[48:96] + q[:48] + q[144:192] + q[96:144]
+
+
+def test_hash_to_g1_program():
+    """PointG1.hashToCurve on the emulator against the reference's kilic / RFC random-oracle vectors (hashToCurve.test.ts)."""
+    import json
+    d = json.load(open(os.path.join(GOLDEN, "hash_to_curve.json")))
+    b = vmcompile.compile_program("hash_to_g1")
+    for key in ("g1_kilic_ro", "g1_rfc_ro"):
+        dst = d[key]["dst"].encode("latin1")
+        vecs = d[key]["vectors"]
+        n = len(vecs)
+        uniform = bytearray(b"".join(O.expand_message_xmd(v["msg"].encode("latin1"), dst, 128) for v in vecs))
+        out = bytearray(96 * n)
+        emu.run_program(b, {0: (uniform, 128), 2: (out, 96)}, n)
+        for i, v in enumerate(vecs):
+            assert bytes(out[96 * i: 96 * i + 96]).hex() == v["expected"], (key, i)
