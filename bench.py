@@ -1,14 +1,23 @@
 #!/usr/bin/env python3
-"""bench.py -- pairings/sec of the B200 engine on BASELINE.json's config 2 (65 536 independent pairings).
+"""bench.py -- pairings/sec and verifyBatch / sign sigs/sec of the B200 engine on BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n ITEMS] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n ITEMS] [--impl reference] [--full-parity]
 
-One "step" = one pass of the hot path (Miller loop + final exponentiation) over one batch of N_ITEMS
-synthetic pairings (i*G1, i*G2) -- the reference's kilic fixtures are the first 1000 items and are
-byte-compared.  `value` = whole-job pairings/s with inputs resident in HBM (CUDA events on the launching
-stream, max over ranks); `e2e` = the same through the C-ABI host entry point with host buffers
-(H2D + kernel + D2H inside the timed region).  Multi-GPU: independent pairings shard by index, no
-collective on the data path ("weak" scaling: every rank processes N_ITEMS).
+Headline (`metric`, `value`): config 2, 65 536 independent pairings per GPU.  One "step" = one pass of the hot path (Miller
+loop + final exponentiation) over the batch.  Inputs follow SURVEY 8d: the reference's 1000 kilic pairs (i G1, i G2) as
+prefix, then P_i = a_i G1, Q_i = b_i G2 with scalars from a SHA-256 counter-mode PRNG (seed 0xB200 + rank).  `value` =
+whole-job pairings/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` = the same
+through the C-ABI host entry point with pinned host buffers (H2D + kernel + D2H inside the timed region).  `parity` = EVERY
+output of the timed batch byte-compared with the C oracle (n_ok / n), the prefix also with the reference's fixture file.
+Further sections of the same JSON line:
+    verify_batch         config 3 (262 144 signatures per GPU; 8 GPUs = config 5, weak scaling) incl. negative controls at size
+    verify_batch_strong  config 5 as a fixed 2 097 152-signature batch over the N GPUs (strong scaling) + the bit-for-bit check
+                         "sharded result == single-GPU result" on the un-exponentiated 576 bytes
+    sign                 config 4 (1 048 576 signatures, one GPU): KAT prefix + strided sample (or --full-parity: all) vs the C oracle
+    table                the rows of BASELINE.md section 3
+Multi-GPU: one process per GPU (torchrun); independent pairings shard by index with no collective; verifyBatch exchanges the
+device-resident 576-byte partial products with ONE NCCL all-gather (no host bounce).  tools/bench_multi.py measures the
+in-process multi-GPU entry point (bls381_verify_batch_multi) the Node addon uses.
 """
 import argparse
 import json

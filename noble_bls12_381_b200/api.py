@@ -14,6 +14,12 @@ reference's own tests (test/index.test.ts, test/pairing.test.ts):
 `Hex` = bytes | bytearray | hex str.  Points are thin value objects holding AFFINE wire bytes (or infinity);
 all group / field arithmetic runs on the device through the C ABI (include/bls381_b200.h).  The reference's
 async functions are plain synchronous functions here.  There is no CPU fallback.
+
+Known deviations from the reference (none on the verify / verifyBatch / sign / aggregate* path):
+  * points are always affine: `aggregate*` on Point inputs and `sign(PointG2, ...)` return the normalised point, equal under
+    `.equals()` / `toHex()` but not field-for-field identical to the reference's un-normalised projective result (SURVEY 8b);
+  * `PointG1.add` / `PointG2.add` go through the device's aggregate path, which decodes with the subgroup check: adding a point
+    that is on the curve but outside the prime-order subgroup raises here, the reference adds it silently (math.ts:993-1025).
 """
 from __future__ import annotations
 
@@ -39,7 +45,7 @@ class utils:  # index.ts:94-145 (only the parts that touch the path)
 
 
 def _dst() -> bytes:
-    return bytes(ord(c) for c in _htf["DST"])  # stringToBytes index.ts:166-172 (charCode per char)
+    return bytes(ord(c) & 0xFF for c in _htf["DST"])  # stringToBytes index.ts:166-172: charCodeAt per char into a Uint8Array (mod 256)
 
 
 def _eng():
@@ -129,11 +135,12 @@ class PointG1:
                 return PointG1.ZERO
             _raise_status(st[0], "G1")
             return PointG1(int.from_bytes(out[:48], "big"), int.from_bytes(out[48:], "big"))
-        if len(b) == 96:
-            if b[0] & 0x40:
+        if len(b) == 96:  # index.ts:315-325 on the device: infinity flag, coordinates reduced by `new Fp`, assertValidity
+            out, st = _eng().g1_from_uncompressed_batch(b, 1)
+            if st[0] == ST_INFINITY:
                 return PointG1.ZERO
-            p = PointG1(int.from_bytes(b[:48], "big") % P, int.from_bytes(b[48:], "big") % P)
-            return p.assertValidity()
+            _raise_status(st[0], "G1")
+            return PointG1(int.from_bytes(out[:48], "big"), int.from_bytes(out[48:], "big"))
         raise ValueError("Invalid point G1, expected 48/96 bytes")
 
     def assertValidity(self) -> "PointG1":
@@ -189,32 +196,12 @@ class PointG1:
     multiplyPrecomputed = multiply
 
     @staticmethod
-    def fromPrivateKey(pk) -> "PointG1":  # index.ts:351-353; key generation is host-side
+    def fromPrivateKey(pk) -> "PointG1":  # index.ts:351-353
+        """BASE * normalizePrivKey(pk) on the device (constant-time fixed-window ladder, vmprog/curves.py mul_secret): the
+        reference's precomputed wNAF table (math.ts:1086-1167) yields the same point; no secret-dependent host arithmetic."""
         k = normalizePrivKey(pk)
-        acc, d = None, (PointG1.BASE.x, PointG1.BASE.y)
-        while k:
-            if k & 1:
-                acc = _aff_add(acc, d)
-            d = _aff_add(d, d)
-            k >>= 1
-        return PointG1(acc[0], acc[1])
-
-
-def _aff_add(p, q):
-    """Affine group law on G1 with Python ints (host-side key generation only)."""
-    if p is None:
-        return q
-    if q is None:
-        return p
-    (x1, y1), (x2, y2) = p, q
-    if x1 == x2:
-        if (y1 + y2) % P == 0:
-            return None
-        lam = 3 * x1 * x1 * pow(2 * y1, -1, P) % P
-    else:
-        lam = (y2 - y1) * pow(x2 - x1, -1, P) % P
-    x3 = (lam * lam - x1 - x2) % P
-    return x3, (lam * (x1 - x3) - y1) % P
+        out, fl = _eng().g1_scalar_mul_batch(PointG1.BASE.wire(), k.to_bytes(32, "big"), 1)
+        return PointG1.ZERO if fl[0] & 2 else PointG1(int.from_bytes(out[:48], "big"), int.from_bytes(out[48:], "big"))
 
 
 PointG1.BASE = PointG1(
@@ -248,9 +235,13 @@ class PointG2:
     def fromSignature(h) -> "PointG2":  # index.ts:500-530
         b = _ensure_bytes(h)
         if len(b) == 192:
-            if (int.from_bytes(b[:96], "big") >> (382 + 384)) & 1:
+            # index.ts:503-514 with half = 96: z1 / z2 are the two 96-byte halves read as ONE number each; the flags are bits
+            # 382 / 381 of z1, x = (z2 mod p, (z1 mod 2^381) mod p).  Re-encode as the 96-byte form and decode that.
+            z1, z2 = int.from_bytes(b[:96], "big"), int.from_bytes(b[96:], "big")
+            if (z1 >> 382) & 1:
                 return PointG2.ZERO
-            raise ValueError("192-byte uncompressed signatures: use PointG2.fromHex")
+            hi = (z1 % (1 << 381)) % P + (((z1 >> 381) & 1) << 381) + (1 << 383)
+            b = hi.to_bytes(48, "big") + (z2 % P).to_bytes(48, "big")
         if len(b) != 96:
             raise ValueError("Invalid compressed signature length, must be 96 or 192")
         out, st = _eng().g2_decompress_batch(b, 1)
@@ -265,13 +256,23 @@ class PointG2:
         m = b[0] & 0xE0
         if m in (0x20, 0x60, 0xE0):
             raise ValueError(f"Invalid encoding flag: {m}")
-        if len(b) == 192 and not (m & 0x80):
-            if b[0] & 0x40:
+        if len(b) == 192 and not (m & 0x80):  # index.ts:563-579 on the device
+            out, st = _eng().g2_from_uncompressed_batch(b, 1)
+            if st[0] == ST_INFINITY:
                 return PointG2.ZERO
-            x1, x0, y1, y0 = (int.from_bytes(b[48 * i : 48 * i + 48], "big") % P for i in range(4))
-            return PointG2((x0, x1), (y0, y1)).assertValidity()
+            _raise_status(st[0], "G2")
+            return PointG2._from_wire(out)
         if len(b) == 96 and (m & 0x80):
-            return PointG2.fromSignature(b)
+            # index.ts:542-562: an infinity flag requires an all-zero body, the square root picks the sign bit, and there is
+            # NO assertValidity (a decodable point outside the subgroup is returned)
+            if m & 0x40:
+                if any(b[1:]) or (b[0] & 0x1F):
+                    raise ValueError("Invalid compressed G2 point")
+                return PointG2.ZERO
+            out, st = _eng().g2_decompress_batch(b, 1)
+            if st[0] == ST_NO_SQRT:
+                raise ValueError("Invalid compressed G2 point")
+            return PointG2._from_wire(out)
         raise ValueError("Invalid point G2, expected 96/192 bytes")
 
     @staticmethod

@@ -205,3 +205,52 @@ def test_full_size_properties(bls):
     for i in (0, 1, 31, 32, 99999, n - 1):
         m = hashlib.sha256(i.to_bytes(8, "big")).digest()
         assert sigs[96 * i : 96 * i + 96] == O.sign(m, i + 1)
+
+
+def test_decoders_follow_the_reference_on_edge_encodings(bls):
+    """PointG2.fromHex(96 B compressed) has its own rules (index.ts:542-562: infinity needs a zero body, no
+    assertValidity), PointG2.fromSignature parses 192-byte input (index.ts:503-514), DST characters are taken mod 256
+    (index.ts:166-172), fromPrivateKey runs on the device."""
+    from oracle import noble_oracle as O
+    g2c = open(os.path.join(GOLDEN, "zkcrypto_g2_compressed.dat"), "rb").read()
+    g2u = open(os.path.join(GOLDEN, "zkcrypto_g2_uncompressed.dat"), "rb").read()
+    for i in (1, 2, 77, 999):
+        pt = bls.PointG2.fromHex(g2c[96 * i: 96 * i + 96])
+        ref = O.g2_from_hex(g2c[96 * i: 96 * i + 96])
+        (x0, x1), (y0, y1) = O.pt_to_affine(O.G2, ref)
+        assert (pt.x, pt.y) == ((x0, x1), (y0, y1))
+        assert bls.PointG2.fromHex(g2u[192 * i: 192 * i + 192]).equals(pt)
+    assert bls.PointG2.fromHex(g2c[:96]).isZero() and bls.PointG2.fromHex(g2u[:192]).isZero()
+    with pytest.raises(ValueError, match="Invalid compressed G2 point"):
+        bls.PointG2.fromHex(bytes([0xC0]) + bytes(94) + b"\x01")      # infinity flag with a non-zero body
+    with pytest.raises(ValueError, match="Invalid encoding flag"):
+        bls.PointG2.fromHex(bytes([0x20]) + g2u[193: 192 * 2])
+    # a decodable point outside the subgroup: fromHex returns it (no assertValidity), fromSignature rejects it
+    xx = (1, 1)
+    while True:
+        xx = (xx[0] + 1, xx[1])
+        yy = O.fp2_sqrt(O.fp2_add(O.fp2_pow(xx, 3), O.B2))
+        if yy is not None and not O.g2_is_torsion_free((xx, yy, O.FP2_ONE)):
+            break
+    enc = (xx[1] + (1 << 383)).to_bytes(48, "big") + xx[0].to_bytes(48, "big")
+    assert bls.PointG2.fromHex(enc).x == xx
+    with pytest.raises(ValueError, match="prime-order subgroup"):
+        bls.PointG2.fromSignature(enc)
+    # 192-byte input of fromSignature: the two 96-byte halves are read as one number each
+    sig = g2c[96 * 5: 96 * 6]
+    wide = bytes(48) + sig[:48] + bytes(48) + sig[48:]
+    assert bls.PointG2.fromSignature(wide).equals(bls.PointG2.fromSignature(sig))
+    ref = O.g2_from_signature(wide)
+    assert bls.PointG2.fromSignature(wide).x == O.pt_to_affine(O.G2, ref)[0]
+    # DST characters above 255 wrap (stringToBytes writes charCodes into a Uint8Array)
+    old = bls.utils.getDSTLabel()
+    try:
+        bls.utils.setDSTLabel("ABŁC")        # U+0141 -> 0x41
+        a = bls.sign(b"msg", 7)
+        bls.utils.setDSTLabel("ABAC")
+        assert bls.sign(b"msg", 7) == a
+    finally:
+        bls.utils.setDSTLabel(old)
+    g1c = open(os.path.join(GOLDEN, "zkcrypto_g1_compressed.dat"), "rb").read()
+    assert bls.PointG1.fromPrivateKey(321).toRawBytes(True) == g1c[48 * 321: 48 * 322]
+    assert bls.getPublicKey((321).to_bytes(32, "big")) == g1c[48 * 321: 48 * 322]
