@@ -217,15 +217,33 @@ napi_value GetPublicKeyBatch(napi_env env, napi_callback_info info) {
 }
 
 // hashToG2(packedMsgs: Uint8Array, offsets: BigUint64Array(n+1), dst: Uint8Array) -> Uint8Array(n*192)  (PointG2.hashToCurve, :481-490)
-napi_value HashToG2(napi_env env, napi_callback_info info) {
+// hashToG1(packedMsgs, offsets, dst) -> Uint8Array(n*96)                                                 (PointG1.hashToCurve, :331-339)
+template <int OUT, int (*FN)(const uint8_t*, const uint64_t*, size_t, const uint8_t*, size_t, uint8_t*)>
+napi_value HashToCurve(napi_env env, napi_callback_info info) {
   size_t argc = 3; napi_value a[3];
   napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
   Bytes msgs, dst; std::vector<uint64_t> off;
   if (argc < 3 || !get_bytes(env, a[0], &msgs) || !get_offsets(env, a[1], msgs.n, &off) || !get_bytes(env, a[2], &dst)) return nullptr;
   const size_t n = off.size() - 1;
-  if (n == 0) return range(env, "hashToG2: empty batch");
-  uint8_t* out; napi_value r = make_u8(env, n * 192, &out);
-  if (bls381_hash_to_g2_batch(msgs.p, off.data(), n, dst.p, dst.n, out) != 0) return fail(env);
+  if (n == 0) return range(env, "hashToCurve: empty batch");
+  uint8_t* out; napi_value r = make_u8(env, n * OUT, &out);
+  if (FN(msgs.p, off.data(), n, dst.p, dst.n, out) != 0) return fail(env);
+  return r;
+}
+
+// g1Encode(points: Uint8Array(n*96), compressed: boolean) -> Uint8Array(n*48 | n*96)     (PointG1#toRawBytes, :355-376)
+// g2Encode(points: Uint8Array(n*192), compressed: boolean) -> Uint8Array(n*96 | n*192)   (PointG2#toSignature / toRawBytes, :586-631)
+template <int PT, int (*FN)(const uint8_t*, size_t, int, uint8_t*)>
+napi_value Encode(napi_env env, napi_callback_info info) {
+  size_t argc = 2; napi_value a[2];
+  napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+  Bytes pts; bool compressed = false;
+  if (argc < 2 || !get_bytes(env, a[0], &pts)) return nullptr;
+  if (napi_get_value_bool(env, a[1], &compressed) != napi_ok) { napi_throw_type_error(env, nullptr, "encode: boolean expected"); return nullptr; }
+  const size_t n = pts.n / PT;
+  if (n == 0 || pts.n != n * PT) return range(env, "encode: bad input length");
+  uint8_t* out; napi_value r = make_u8(env, n * (compressed ? PT / 2 : PT), &out);
+  if (FN(pts.p, n, compressed ? 1 : 0, out) != 0) return fail(env);
   return r;
 }
 
@@ -339,7 +357,12 @@ NAPI_MODULE_INIT() {
   EXPORT("g1ScalarMul", (ScalarMul<96, bls381_g1_scalar_mul_batch>))
   EXPORT("g2ScalarMul", (ScalarMul<192, bls381_g2_scalar_mul_batch>))
   EXPORT("getPublicKeyBatch", GetPublicKeyBatch)
-  EXPORT("hashToG2", HashToG2)
+  EXPORT("hashToG2", (HashToCurve<192, bls381_hash_to_g2_batch>))
+  EXPORT("hashToG1", (HashToCurve<96, bls381_hash_to_g1_batch>))
+  EXPORT("g1FromUncompressed", (Decompress<96, 96, bls381_g1_from_uncompressed_batch>))
+  EXPORT("g2FromUncompressed", (Decompress<192, 192, bls381_g2_from_uncompressed_batch>))
+  EXPORT("g1Encode", (Encode<96, bls381_g1_encode_batch>))
+  EXPORT("g2Encode", (Encode<192, bls381_g2_encode_batch>))
   EXPORT("verifyBatch", VerifyBatch)
   EXPORT("signBatch", SignBatch)
   EXPORT("deviceCount", DeviceCount)

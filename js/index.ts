@@ -224,3 +224,50 @@ export function aggregateSignatures(signatures: G2Hex[]): Uint8Array | ref.Point
 
 /** GPUs the addon shards verifyBatch over (BLS381_B200_DEVICES bit mask; bls381_verify_batch_multi). */
 export const deviceCount = (): number => native.deviceCount();
+
+// ---- batch forms of the (de)serialisers and of hashToCurve (SURVEY 8f): one device call for n inputs -------------------
+const g1FromWire = (w: Uint8Array): ref.PointG1 =>
+  w.every((b) => b === 0) ? ref.PointG1.ZERO : new ref.PointG1(ref.Fp.fromBytes(w.subarray(0, 48)), ref.Fp.fromBytes(w.subarray(48, 96)), ref.Fp.ONE);
+const g2FromWire = (w: Uint8Array): ref.PointG2 =>
+  w.every((b) => b === 0) ? ref.PointG2.ZERO : new ref.PointG2(ref.Fp2.fromBytes(w.subarray(0, 96)), ref.Fp2.fromBytes(w.subarray(96, 192)), ref.Fp2.ONE);
+
+/** PointG1.fromHex (index.ts:298-327) + assertValidity for n encodings of ONE length (48 compressed or 96 uncompressed). */
+export function pointsG1FromHex(hexes: Hex[]): ref.PointG1[] {
+  const bytes = hexes.map(toBytes);
+  const len = bytes.length ? bytes[0].length : 0;
+  if ((len !== 48 && len !== 96) || bytes.some((b) => b.length !== len)) throw new Error('Invalid point G1, expected 48/96 bytes');   // :326
+  const { points, status } = len === 48 ? native.g1Decompress(concat(...bytes)) : native.g1FromUncompressed(concat(...bytes));
+  return bytes.map((_, i) => { raise(status[i], 'G1'); return status[i] === ST_INFINITY ? ref.PointG1.ZERO : g1FromWire(points.subarray(96 * i, 96 * i + 96)); });
+}
+/** PointG2.fromSignature / fromHex (index.ts:500-580) + assertValidity for n encodings of ONE length (96 or 192). */
+export function pointsG2FromHex(hexes: Hex[]): ref.PointG2[] {
+  const bytes = hexes.map(toBytes);
+  const len = bytes.length ? bytes[0].length : 0;
+  if ((len !== 96 && len !== 192) || bytes.some((b) => b.length !== len)) throw new Error('Invalid compressed signature length, must be 96 or 192');   // :504
+  const { points, status } = len === 96 ? native.g2Decompress(concat(...bytes)) : native.g2FromUncompressed(concat(...bytes));
+  return bytes.map((_, i) => { raise(status[i], 'G2'); return status[i] === ST_INFINITY ? ref.PointG2.ZERO : g2FromWire(points.subarray(192 * i, 192 * i + 192)); });
+}
+/** PointG1#toRawBytes(isCompressed) (index.ts:355-376) for n points. */
+export function pointsG1ToRawBytes(points: ref.PointG1[], isCompressed = false): Uint8Array[] {
+  const w = isCompressed ? 48 : 96;
+  const out: Uint8Array = native.g1Encode(concat(...points.map((P) => (P.isZero() ? new Uint8Array(96) : g1Wire(P)))), isCompressed);
+  return points.map((_, i) => out.slice(w * i, w * i + w));
+}
+/** PointG2#toSignature (compressed, index.ts:586-606) / toRawBytes (index.ts:608-631) for n points. */
+export function pointsG2ToRawBytes(points: ref.PointG2[], isCompressed = false): Uint8Array[] {
+  const w = isCompressed ? 96 : 192;
+  const out: Uint8Array = native.g2Encode(concat(...points.map((Q) => (Q.isZero() ? new Uint8Array(192) : g2Wire(Q)))), isCompressed);
+  return points.map((_, i) => out.slice(w * i, w * i + w));
+}
+/** PointG2.hashToCurve (index.ts:481-490) for n messages with the current DST. */
+export function hashToCurveG2Batch(messages: Hex[]): ref.PointG2[] {
+  const { packed, off } = packMessages(messages.map(toBytes));
+  const out: Uint8Array = native.hashToG2(packed, off, dstBytes());
+  return messages.map((_, i) => g2FromWire(out.subarray(192 * i, 192 * i + 192)));
+}
+/** PointG1.hashToCurve (index.ts:331-339) for n messages with the current DST. */
+export function hashToCurveG1Batch(messages: Hex[]): ref.PointG1[] {
+  const { packed, off } = packMessages(messages.map(toBytes));
+  const out: Uint8Array = native.hashToG1(packed, off, dstBytes());
+  return messages.map((_, i) => g1FromWire(out.subarray(96 * i, 96 * i + 96)));
+}

@@ -633,6 +633,7 @@ struct Nccl {
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     nccl_comm_t comms[kMaxDevices] = {};
+    int ncomms = 0;  // number of devices the communicators were created for
     bool ready = false;
     std::string why;  // why NCCL is not used (peer copies instead)
 };
@@ -663,11 +664,15 @@ void nccl_load() {
 
 void multi_shutdown() {
     if (g_nccl.ready) {
-        for (int j = 0; j < g_ncontexts; ++j)
+        for (int j = 0; j < g_nccl.ncomms; ++j)
             if (g_nccl.comms[j]) g_nccl.CommDestroy(g_nccl.comms[j]);
+        for (int j = 0; j < kMaxDevices; ++j) g_nccl.comms[j] = nullptr;
+        g_nccl.ncomms = 0;
         g_nccl.ready = false;
     }
 }
+
+std::mutex g_multi_mu;  // one multi-device call at a time (the partials live in per-context staging buffers)
 
 }  // namespace
 
@@ -1095,18 +1100,27 @@ int bls381_init_devices(uint32_t device_mask, const char* program_dir) {
         g_cur = prev;
         if (rc) return rc;
     }
+    std::lock_guard<std::mutex> multi_lock(g_multi_mu);
     g_ncontexts = std::max(g_ncontexts, nd);
-    if (nd > 1 && !g_nccl.ready) {
+    if (g_ncontexts > 1 && g_nccl.ncomms != g_ncontexts) {
+        // the communicators span exactly the current set of contexts: rebuilt when devices are added
+        multi_shutdown();
         nccl_load();
+        int all[kMaxDevices];
+        for (int j = 0; j < g_ncontexts; ++j) all[j] = g_states[j].device;
         if (g_nccl.handle) {
-            const int rc = g_nccl.CommInitAll(g_nccl.comms, nd, devs);
-            if (rc == 0) g_nccl.ready = true;
-            else g_nccl.why = std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+            const int rc = g_nccl.CommInitAll(g_nccl.comms, g_ncontexts, all);
+            if (rc == 0) {
+                g_nccl.ready = true;
+                g_nccl.ncomms = g_ncontexts;
+            } else {
+                g_nccl.why = std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+            }
         }
         if (!g_nccl.ready) {  // fallback transport: peer-to-peer copies into the first device
-            for (int j = 1; j < nd; ++j) {
-                cudaSetDevice(devs[0]);
-                cudaDeviceEnablePeerAccess(devs[j], 0);
+            for (int j = 1; j < g_ncontexts; ++j) {
+                cudaSetDevice(all[0]);
+                cudaDeviceEnablePeerAccess(all[j], 0);
                 cudaGetLastError();
             }
         }
@@ -1117,8 +1131,6 @@ int bls381_init_devices(uint32_t device_mask, const char* program_dir) {
 
 int bls381_device_count(void) { return g_ncontexts; }
 const char* bls381_multi_transport(void) { return g_nccl.ready ? "nccl" : (g_ncontexts > 1 ? "peer-copy" : "single-device"); }
-
-static std::mutex g_multi_mu;  // one multi-device call at a time (the partials live in per-context staging buffers)
 
 int bls381_verify_batch_multi(const uint8_t* sig96, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* pks48,
                               size_t n, const uint8_t* dst, size_t dst_len, int* verdict, int32_t* status) {

@@ -30,7 +30,7 @@ def main(trace_path, program_path):
     cls = collections.defaultdict(list)
     for w in range(W):
         for r in range(nrec):
-            hdr, = struct.unpack_from("<I", img, base + (w * nrec + r) * 128)
+            hdr, = struct.unpack_from("<I", img, base + (w * nrec + r) * 256)
             key = (hdr & 0xFF, (hdr >> 16) & 0xF, (hdr >> 20) & 3, (hdr >> 22) & 7)
             cls[key].append(t[0, w, r])
     print("op class (opcode, T, E, ncorr): count, mean exec, mean phases")
