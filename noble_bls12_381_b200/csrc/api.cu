@@ -17,6 +17,7 @@
 #include "../../include/bls381_b200.h"
 #include "vm_kernel.cu"  // single translation unit: the interpreter kernel
 #include "sha256_xmd.cuh"
+#include "swu_g2.cuh"     // hash_to_field + SWU map for G2 as a plain kernel (the serial square-root chains)
 
 namespace {
 
@@ -45,7 +46,7 @@ struct State {
     int dynamic_batches = 1;  // batches claimed from a global counter (+4.9 % at 65536 pairings, profiles/r1_notes.md)
     unsigned long long* d_clk = nullptr;  // clock probe of the last tower-VM launch {cycles, ns}
     // grow-only device staging for the host entry points
-    static constexpr int kStages = 10;
+    static constexpr int kStages = 11;
     uint8_t* d_stage[kStages] = {};
     size_t stage_bytes[kStages] = {};
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -56,6 +57,7 @@ struct State {
     int force_ctas = 0;  // tuning override (env BLS381_B200_CTAS)
     int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
+    int swu_kernel = 1;  // hash-to-curve front (hash_to_field + SWU) as the hand-written kernel; 0 = all inside the tower-VM program (A/B)
     // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
     // verifyBatch at 131072 signatures on a B200: 1.26 / 1.39 / 1.42 / 1.40 M sigs/s for 1 / 2 / 3 / 4
     int pairs_per_lane = 3;
@@ -453,6 +455,16 @@ int run3(const char* prog, uint8_t* in, uint32_t in_stride, uint8_t* out, uint32
     return vm_run(prog, bufs, strides, 6, n, s);
 }
 
+// g.d_stage[4] (n x 256 uniform bytes) -> g.d_stage[10] (n x 576 B: the two points of E' per message), csrc/swu_g2.cuh
+int swu_points(size_t n, cudaStream_t s) {
+    int rc;
+    if ((rc = stage(10, n * 576))) return rc;
+    swu::swu_g2_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(g.d_stage[4], g.d_stage[10], 2 * n);
+    CUDA_TRY(cudaGetLastError());
+    g.launches.fetch_add(1);
+    return BLS381_OK;
+}
+
 // msgs (device, packed) -> n x 192 B affine H(m) at d_out
 int hash_to_g2_dev(const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const uint8_t* dst, size_t dst_len,
                    uint8_t* d_out, cudaStream_t s) {
@@ -463,9 +475,10 @@ int hash_to_g2_dev(const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[5], dp.data(), dp.size(), cudaMemcpyHostToDevice, s));
     xmd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_msgs, d_off, n, g.d_stage[5], (uint32_t)dp.size(), g.d_stage[4]);
     CUDA_TRY(cudaGetLastError());
-    return run3("hash_to_g2", g.d_stage[4], 256, d_out, 192, nullptr, n, s);
+    if (!g.swu_kernel) return run3("hash_to_g2", g.d_stage[4], 256, d_out, 192, nullptr, n, s);
+    if ((rc = swu_points(n, s))) return rc;
+    return run3("h2g2_tail", g.d_stage[10], 576, d_out, 192, nullptr, n, s);
 }
-
 
 // OR the compression flag bits (index.ts:26-28) into byte 0 of each compressed body
 __global__ void apply_flags_kernel(uint8_t* body, uint32_t stride, const int32_t* flags, size_t n) {
@@ -573,6 +586,7 @@ int init_context(int device, const char* program_dir) {   // caller holds g.mu; 
     if (const char* e = getenv("BLS381_B200_CTAS")) g.force_ctas = atoi(e);
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
+    if (const char* e = getenv("BLS381_B200_SWU_KERNEL")) g.swu_kernel = atoi(e);
     if (const char* e = getenv("BLS381_B200_PAIRS_PER_LANE")) g.pairs_per_lane = atoi(e);
     if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
     if (const char* e = getenv("BLS381_B200_LOG_LAUNCHES")) g.log_launches = atoi(e);
@@ -718,6 +732,7 @@ int bls381_set_option(const char* name, int value) {
     else if (n == "ctas_per_sm") g.force_ctas = value;
     else if (n == "poll_sleep_ns") g.sleep_ns = value;
     else if (n == "no_tma") g.no_tma = value != 0;
+    else if (n == "swu_kernel") g.swu_kernel = value != 0;
     else if (n == "pairs_per_lane") g.pairs_per_lane = value;
     else return fail(BLS381_EINVAL, "unknown option: " + n);
     return BLS381_OK;
@@ -1340,9 +1355,16 @@ int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t*
     CUDA_TRY(cudaGetLastError());
     base_z_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[7], n);
     CUDA_TRY(cudaGetLastError());
-    uint8_t* bufs[6] = {g.d_stage[4], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
-    uint32_t strides[6] = {256, 32, 96, 0, 0, 4};
-    if ((rc = vm_run("sign", bufs, strides, 6, n, s))) return rc;
+    if (g.swu_kernel) {
+        if ((rc = swu_points(n, s))) return rc;
+        uint8_t* bufs[6] = {g.d_stage[10], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
+        uint32_t strides[6] = {576, 32, 96, 0, 0, 4};
+        if ((rc = vm_run("sign_tail", bufs, strides, 6, n, s))) return rc;
+    } else {
+        uint8_t* bufs[6] = {g.d_stage[4], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
+        uint32_t strides[6] = {256, 32, 96, 0, 0, 4};
+        if ((rc = vm_run("sign", bufs, strides, 6, n, s))) return rc;
+    }
     apply_flags_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[2], 96, (const int32_t*)g.d_stage[6], n);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(g.ev1, s));

@@ -42,12 +42,13 @@ def image(b) -> bytes:
 # ingest programs are serial Fp2 chains: fewer warps per CTA, more CTAs per SM
 INGEST_WARPS = {"g1_decompress": 2, "g2_decompress": 4, "hash_to_g2": 4, "sign": 4, "g1_sum_affine": 4, "g1_sum_proj": 4,
                 "g2_sum_affine": 4, "g2_sum_proj": 4, "g1_compress": 2, "g2_compress": 2, "g1_validate": 2, "g2_validate": 4,
-                "g2_scalar_mul": 4, "g1_scalar_mul": 4, "g1_from_uncompressed": 2, "g2_from_uncompressed": 4, "hash_to_g1": 2}
+                "g2_scalar_mul": 4, "g1_scalar_mul": 4, "g1_from_uncompressed": 2, "g2_from_uncompressed": 4, "hash_to_g1": 2,
+                "h2g2_tail": 4, "sign_tail": 4}
 # shared-memory slots per CTA: the serial ingest programs run more CTAs per SM with fewer slots each (cold values go to the
 # L2-resident far slots); measured on a B200: hash_to_g2 / sign / g2_decompress 4 CTAs x 4 warps instead of 2 x 4
 # (sign +13 %, verifyBatch +7 %), g1_decompress 8 CTAs x 2 warps instead of 3 x 2 (verifyBatch +9 %)
 # the scalar-multiplication window tables (16 points) are cold: they live in far slots
-INGEST_SLOTS = {"hash_to_g1": 16, "hash_to_g2": 28, "sign": 28, "g2_decompress": 33, "g1_decompress": 16, "g2_scalar_mul": 33, "g1_scalar_mul": 24}
+INGEST_SLOTS = {"hash_to_g1": 16, "hash_to_g2": 28, "sign": 28, "h2g2_tail": 28, "sign_tail": 28, "g2_decompress": 33, "g1_decompress": 16, "g2_scalar_mul": 33, "g1_scalar_mul": 24}
 ALL_PROGRAMS = dict(tower.PROGRAMS)
 ALL_PROGRAMS.update(curves.PROGRAMS)
 

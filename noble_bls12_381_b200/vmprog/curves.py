@@ -717,6 +717,39 @@ def _hash_to_g2_projective(ig: Ingest, buf: int):
     return ig.g2_clear_cofactor(e)
 
 
+def _e1_points_in(ig: Ingest, buf: int):
+    """The two points of E' per message written by swu_g2_kernel (csrc/swu_g2.cuh): 12 Montgomery residues, 48 bytes
+    big-endian each, (X.c0, X.c1, Y.c0, Y.c1, Z.c0, Z.c1) of SWU(u0) then of SWU(u1)."""
+    b = ig.b
+    f = [Lin.of(b.inp_bytes(buf, 48 * k, 48, montgomery=False)) for k in range(12)]
+    return tuple((E2(f[6 * j], f[6 * j + 1]), E2(f[6 * j + 2], f[6 * j + 3]), E2(f[6 * j + 4], f[6 * j + 5])) for j in range(2))
+
+
+def _hash_tail_projective(ig: Ingest, buf: int):
+    """Second half of PointG2.hashToCurve (index.ts:484-489): P0 + P1, the 3-isogeny, clearCofactor."""
+    p0, p1 = _e1_points_in(ig, buf)
+    s = _add_generic(ig, p0, p1)
+    e = _isogeny3_projective(ig, s)
+    return ig.g2_clear_cofactor(e)
+
+
+def build_h2g2_tail(warps=4) -> Builder:
+    """buffer 0: n x 576 B (two points of E' per message, from swu_g2_kernel) -> buffer 2: n x 192 B affine H(m)."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    h = _hash_tail_projective(ig, BUF_IN)
+    x, y = ig.g2_to_affine(h)
+    b.out(x.c0, BUF_OUT, 0)
+    b.out(x.c1, BUF_OUT, 1)
+    b.out(y.c0, BUF_OUT, 2)
+    b.out(y.c1, BUF_OUT, 3)
+    return b
+
+
+PROGRAMS["h2g2_tail"] = build_h2g2_tail
+
+
 def build_hash_to_g2(warps=8) -> Builder:
     """buffer 0: n x 256 B uniform bytes -> buffer 2: n x 192 B affine H(m) (x.c0, x.c1, y.c0, y.c1)."""
     b = Builder(warps)
@@ -899,6 +932,20 @@ def build_sign(warps=8) -> Builder:
     return b
 
 
+def build_sign_tail(warps=4) -> Builder:
+    """sign() behind the SWU kernel: buffer 0: n x 576 B (two points of E' per message), buffers 1, 2, 5 as in `sign`."""
+    b = Builder(warps)
+    t = Tower(b)
+    ig = Ingest(t)
+    h = _hash_tail_projective(ig, BUF_IN)
+    if SIGN_GLS4:
+        s = ig.g2_mul_secret_gls4(h, lambda i: b.bit(BUF_AUX, 0, 32, i))
+    else:
+        s = ig.G2.mul_secret(h, R_ORDER.bit_length(), lambda i: b.bit(BUF_AUX, 0, 32, i))
+    _g2_compress_out(ig, s)
+    return b
+
+
 def _lane_sum(ig: Ingest, G: Curve, p):
     """Butterfly sum over the 32 lanes with complete additions (every lane ends with the total)."""
     b, F = ig.b, G.F
@@ -979,6 +1026,7 @@ def _build_compress(which: str, warps: int) -> Builder:
 
 PROGRAMS.update({
     "sign": build_sign,
+    "sign_tail": build_sign_tail,
     "g1_sum_affine": lambda w: _build_sum("g1", "affine", w),
     "g1_sum_proj": lambda w: _build_sum("g1", "proj", w),
     "g2_sum_affine": lambda w: _build_sum("g2", "affine", w),

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../noble_bls12_381_b200/csrc/vm.cuh"
 #include "../../noble_bls12_381_b200/csrc/fp_inv.cuh"
+#include "../../noble_bls12_381_b200/csrc/swu_g2.cuh"
 
 extern "C" {
 
@@ -25,6 +26,9 @@ void emu_mac_redc(int n, const uint32_t* a, const uint32_t* b, int rounds, uint3
 
 // n Montgomery-form inversions (fp_inv.cuh)
 void emu_fp_inv(int n, const uint32_t* x, uint32_t* r) { for (int i = 0; i < n; ++i) fpc::fp_inv_mont(r + 12 * i, x + 12 * i); }
+
+// hash_to_field + SWU for G2 (csrc/swu_g2.cuh): n field elements, 128 uniform bytes in, 288 bytes out each
+void emu_swu_g2(const uint8_t* in, uint8_t* out, size_t n) { for (size_t i = 0; i < n; ++i) swu::swu_g2_one(in + 128 * i, out + 288 * i); }
 
 void emu_add_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::add_mod(r, a, b); }
 void emu_sub_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::sub_mod(r, a, b); }

@@ -169,6 +169,48 @@ def test_hash_to_g2_program():
         assert bytes(out[192 * i : 192 * i + 192]) == b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1)), i
 
 
+def _swu_points(uniform: bytes) -> bytearray:
+    """hash_to_field + SWU of csrc/swu_g2.cuh (host build of the kernel's source): n x 256 uniform bytes -> n x 576 bytes."""
+    import ctypes
+    n2 = len(uniform) // 128
+    out = (ctypes.c_uint8 * (288 * n2))()
+    emu.lib().emu_swu_g2(bytes(uniform), out, ctypes.c_size_t(n2))
+    return bytearray(out)
+
+
+def test_swu_kernel_source_against_the_oracle_map():
+    """map_to_curve_simple_swu_9mod16 (math.ts:1220-1267) of the hand-written kernel: both candidate families, t = 0 (the
+    exceptional denominator), inputs >= p in the 64-byte chunks."""
+    rng = random.Random(5)
+    raws = [bytes(128), O.P.to_bytes(64, "big") * 2, b"\xff" * 128] + [bytes(rng.getrandbits(8) for _ in range(128)) for _ in range(21)]
+    out = _swu_points(b"".join(raws))
+    rinv = pow(1 << 384, -1, O.P)
+    fam = set()
+    for i, raw in enumerate(raws):
+        t = (int.from_bytes(raw[:64], "big") % O.P, int.from_bytes(raw[64:], "big") % O.P)
+        f = [int.from_bytes(out[288 * i + 48 * k: 288 * i + 48 * k + 48], "big") for k in range(6)]
+        assert all(v < O.P for v in f)
+        f = [v * rinv % O.P for v in f]
+        zi = O.fp2_inv((f[4], f[5]))
+        x, y = O.fp2_mul((f[0], f[1]), zi), O.fp2_mul((f[2], f[3]), zi)
+        assert (x, y) == O.map_to_curve_simple_swu_9mod16(t), i
+        fam.add(O.fp2_sqrt(O.fp2_add(O.fp2_add(O.fp2_mul(O.fp2_sqr(x), x), O.fp2_mul((0, 240), x)), (1012, 1012))) is not None)
+    assert fam == {True}  # every output is on E'
+
+
+def test_h2g2_tail_program_behind_the_swu_kernel():
+    """PointG2.hashToCurve as the library runs it: xmd -> SWU kernel -> `h2g2_tail` program."""
+    b = vmcompile.compile_program("h2g2_tail")
+    msgs = [b"", b"abc", bytes(range(32)), b"x" * 100, bytes.fromhex("d2"), b"abcdef0123456789", b"q128_" + b"q" * 128]
+    n = len(msgs)
+    pts = _swu_points(b"".join(O.expand_message_xmd(m, O.DEFAULT_DST, 256) for m in msgs))
+    out = bytearray(192 * n)
+    emu.run_program(b, {0: (pts, 576), 2: (out, 192)}, n)
+    for i, m in enumerate(msgs):
+        (x0, x1), (y0, y1) = O.pt_to_affine(O.G2, O.g2_hash_to_curve(m))
+        assert bytes(out[192 * i : 192 * i + 192]) == b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1)), i
+
+
 def _scalars():
     rng = random.Random(11)
     r = O.R_ORDER
@@ -234,6 +276,28 @@ def test_sign_program_against_reference_kats():
     sks = bytearray(b"".join(digits(int(sk, 16) % O.R_ORDER) for sk, _, _ in lines))
     out, fl = bytearray(96 * n), bytearray(4 * n)
     emu.run_program(b, {0: (xmd, 256), 1: (sks, 32), 2: (out, 96), 5: (fl, 4)}, n)
+    flags = struct.unpack("<%di" % n, fl)
+    for i, (_, _, sig) in enumerate(lines):
+        body = bytearray(out[96 * i : 96 * i + 96])
+        body[0] |= 0x80 | (0x40 if flags[i] & 2 else 0) | (0x20 if flags[i] & 1 else 0)
+        assert bytes(body).hex() == sig.strip().lower(), i
+
+
+def test_sign_tail_program_against_reference_kats():
+    """sign as the library runs it: xmd -> SWU kernel -> `sign_tail` (tail of hash-to-curve + ladder + compression)."""
+    lines = [l.split(":") for l in open(os.path.join(GOLDEN, "sign_g2_vectors.txt")).read().split("\n") if l][6:12]
+    b = vmcompile.compile_program("sign_tail")
+    n = len(lines)
+    pts = _swu_points(b"".join(O.expand_message_xmd(bytes.fromhex(m), O.DEFAULT_DST, 256) for _, m, _ in lines))
+    z = 0xD201000000010000
+
+    def digits(k):
+        a = [(k // z**i) % z for i in range(4)]
+        return b"".join(a[i].to_bytes(8, "big") for i in (3, 2, 1, 0))
+
+    sks = bytearray(b"".join(digits(int(sk, 16) % O.R_ORDER) for sk, _, _ in lines))
+    out, fl = bytearray(96 * n), bytearray(4 * n)
+    emu.run_program(b, {0: (pts, 576), 1: (sks, 32), 2: (out, 96), 5: (fl, 4)}, n)
     flags = struct.unpack("<%di" % n, fl)
     for i, (_, _, sig) in enumerate(lines):
         body = bytearray(out[96 * i : 96 * i + 96])
