@@ -64,6 +64,28 @@ def issued_imad_per_item(program_path, wide_per_product=144):
     return products * wide_per_product + reductions * 156, products, reductions
 
 
+def swu_kernel_imad_per_item():
+    """IMAD.WIDE of swu_g2_kernel (csrc/swu_g2.cuh) per MESSAGE (two field elements): per element two chains a^((p-3)/4)
+    (sliding windows of width 4: the schedule of tools/gen_swu_consts.py), 20 Fp2 products (4 products + 2 reductions each),
+    19 single Fp products and the norm (2 products, 1 reduction); a product = 144, a reduction = 156 IMAD.WIDE."""
+    p = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    bits = bin((p - 3) // 4)[2:]
+    i = nwin = 0
+    while i < len(bits):
+        if bits[i] == "0":
+            i += 1
+            continue
+        j = min(i + 4, len(bits))
+        while bits[j - 1] == "0":
+            j -= 1
+        nwin += 1
+        i = j
+    chain = (len(bits) - 1) + (nwin - 1) + 8  # squarings + multiplications + the table of odd powers
+    products = 2 * chain + 20 * 4 + 19 + 2
+    reductions = 2 * chain + 20 * 2 + 19 + 1
+    return 2 * (products * 144 + reductions * 156), 2 * products, 2 * reductions
+
+
 class ClockSampler:
     """One long-lived `nvidia-smi -lms 50` process (spawning a fresh nvidia-smi per sample takes longer than a step);
     samples are time-stamped so that only those inside the timed region are summarised."""
@@ -564,9 +586,12 @@ def main():
         # per-section issued-multiply rooflines (issued IMAD.WIDE of the program images / kernel time)
         sect = {}
         if sg is not None:
-            iw, pr, rd = issued("sign")
-            sect["sign"] = {"imad_wide_per_item": iw, "products": pr, "reductions": rd,
-                            "issued_frac_sustained": sg["kernel_value"] * iw / imad_sustained}
+            # sign = swu_g2_kernel (hash_to_field + SWU, hand-written) + the tower-VM program sign_tail
+            iw, pr, rd = issued("sign_tail")
+            kw, kp, kr = swu_kernel_imad_per_item()
+            sect["sign"] = {"imad_wide_per_item": iw + kw, "products": pr + kp, "reductions": rd + kr,
+                            "of_which_swu_g2_kernel": {"imad_wide_per_item": kw, "products": kp, "reductions": kr},
+                            "issued_frac_sustained": sg["kernel_value"] * (iw + kw) / imad_sustained}
         line["roofline_sections"] = sect
         cpu = None
         if not args.no_cpu_baseline:

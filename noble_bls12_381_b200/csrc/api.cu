@@ -18,6 +18,7 @@
 #include "vm_kernel.cu"  // single translation unit: the interpreter kernel
 #include "sha256_xmd.cuh"
 #include "swu_g2.cuh"     // hash_to_field + SWU map for G2 as a plain kernel (the serial square-root chains)
+#include "g2_kernels.cuh"  // tail of hash-to-curve and the sign ladder as plain kernels (a thread per item)
 
 namespace {
 
@@ -58,6 +59,7 @@ struct State {
     int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
     int swu_kernel = 1;  // hash-to-curve front (hash_to_field + SWU) as the hand-written kernel; 0 = all inside the tower-VM program (A/B)
+    int tail_kernels = 1;  // tail of hash-to-curve / sign ladder as hand-written kernels (needs swu_kernel); 0 = tower-VM programs h2g2_tail / sign_tail (A/B)
     // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
     // verifyBatch at 131072 signatures on a B200: 1.26 / 1.39 / 1.42 / 1.40 M sigs/s for 1 / 2 / 3 / 4
     int pairs_per_lane = 3;
@@ -477,7 +479,11 @@ int hash_to_g2_dev(const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const
     CUDA_TRY(cudaGetLastError());
     if (!g.swu_kernel) return run3("hash_to_g2", g.d_stage[4], 256, d_out, 192, nullptr, n, s);
     if ((rc = swu_points(n, s))) return rc;
-    return run3("h2g2_tail", g.d_stage[10], 576, d_out, 192, nullptr, n, s);
+    if (!g.tail_kernels) return run3("h2g2_tail", g.d_stage[10], 576, d_out, 192, nullptr, n, s);
+    swu::h2g2_tail_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[10], d_out, n);
+    CUDA_TRY(cudaGetLastError());
+    g.launches.fetch_add(1);
+    return BLS381_OK;
 }
 
 // OR the compression flag bits (index.ts:26-28) into byte 0 of each compressed body
@@ -587,6 +593,7 @@ int init_context(int device, const char* program_dir) {   // caller holds g.mu; 
     if (const char* e = getenv("BLS381_B200_SLEEP_NS")) g.sleep_ns = atoi(e);
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
     if (const char* e = getenv("BLS381_B200_SWU_KERNEL")) g.swu_kernel = atoi(e);
+    if (const char* e = getenv("BLS381_B200_TAIL_KERNELS")) g.tail_kernels = atoi(e);
     if (const char* e = getenv("BLS381_B200_PAIRS_PER_LANE")) g.pairs_per_lane = atoi(e);
     if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
     if (const char* e = getenv("BLS381_B200_LOG_LAUNCHES")) g.log_launches = atoi(e);
@@ -733,6 +740,7 @@ int bls381_set_option(const char* name, int value) {
     else if (n == "poll_sleep_ns") g.sleep_ns = value;
     else if (n == "no_tma") g.no_tma = value != 0;
     else if (n == "swu_kernel") g.swu_kernel = value != 0;
+    else if (n == "tail_kernels") g.tail_kernels = value != 0;
     else if (n == "pairs_per_lane") g.pairs_per_lane = value;
     else return fail(BLS381_EINVAL, "unknown option: " + n);
     return BLS381_OK;
@@ -1355,7 +1363,14 @@ int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t*
     CUDA_TRY(cudaGetLastError());
     base_z_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[7], n);
     CUDA_TRY(cudaGetLastError());
-    if (g.swu_kernel) {
+    bool flags_applied = false;
+    if (g.swu_kernel && g.tail_kernels) {
+        if ((rc = swu_points(n, s))) return rc;
+        swu::sign_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[10], g.d_stage[7], g.d_stage[2], n);
+        CUDA_TRY(cudaGetLastError());
+        g.launches.fetch_add(1);
+        flags_applied = true;  // the kernel writes the finished signature (flag bits included)
+    } else if (g.swu_kernel) {
         if ((rc = swu_points(n, s))) return rc;
         uint8_t* bufs[6] = {g.d_stage[10], g.d_stage[7], g.d_stage[2], nullptr, nullptr, g.d_stage[6]};
         uint32_t strides[6] = {576, 32, 96, 0, 0, 4};
@@ -1365,8 +1380,10 @@ int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t*
         uint32_t strides[6] = {256, 32, 96, 0, 0, 4};
         if ((rc = vm_run("sign", bufs, strides, 6, n, s))) return rc;
     }
-    apply_flags_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[2], 96, (const int32_t*)g.d_stage[6], n);
-    CUDA_TRY(cudaGetLastError());
+    if (!flags_applied) {
+        apply_flags_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g.d_stage[2], 96, (const int32_t*)g.d_stage[6], n);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaEventRecord(g.ev1, s));
     CUDA_TRY(cudaMemcpyAsync(out_sig96, g.d_stage[2], n * 96, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemsetAsync(g.d_stage[7], 0, n * 32, s));  // the scalars / digits do not stay in the pooled staging buffer

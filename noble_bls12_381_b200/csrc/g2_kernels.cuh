@@ -1,0 +1,365 @@
+// Per-item G2 work behind the SWU kernel as plain CUDA kernels (a thread per message / signature):
+//   h2g2_tail_kernel : P0 + P1 on E', the 3-isogeny, clearCofactor, affine          (PointG2.hashToCurve, index.ts:484-489)
+//   sign_kernel      : the same, then sk * H(m) with the constant-time joint ladder and toSignature   (sign, index.ts:746-752)
+//
+// These are long serial chains of Fp2 operations per item (one to four products per micro-op in the tower-VM, where record
+// decode and dataflow waits dominate: 51 - 63 % of the multiplier, profiles/r2_notes.md).  A thread that keeps the
+// multiply-accumulate in registers and its points in local memory runs the same arithmetic at ~85 %.  The tower-VM keeps
+// the Fp12 work (Miller loops, final exponentiation), where a record carries 12 products and a CTA works on one item set.
+//
+// Same formulas as the tower-VM programs (vmprog/curves.py), which remain in the tree as the A/B path
+// (bls381_set_option("tail_kernels", 0)) and as the second implementation the tests compare against:
+//   complete projective addition / doubling (Renes-Costello-Batina 2015, a = 0; the same group element as the reference's
+//   Jacobian add / double with special cases, math.ts:966-1024), psi / psi2 (math.ts:1390-1408), clearCofactor
+//   (index.ts:659-672), the 3-isogeny (math.ts:1315-1325, 1547-1610), add-1998-cmo-2 on E' (math.ts:1008-1024),
+//   toSignature (index.ts:586-598).  The same source compiles for the host (tests/emu).
+#pragma once
+#include "fp_inv.cuh"
+#include "swu_g2.cuh"
+
+namespace swu {
+
+struct G2p { Fe2 X, Y, Z; };
+
+SWU_INL void fe2_sub(Fe2& r, const Fe2& a, const Fe2& b) { fe_sub(r.c0, a.c0, b.c0); fe_sub(r.c1, a.c1, b.c1); }
+SWU_INL void fe2_dbl(Fe2& r, const Fe2& a) { fe2_add(r, a, a); }
+SWU_INL void fe2_conj(Fe2& r, const Fe2& a) { r.c0 = a.c0; fe_neg(r.c1, a.c1); }
+// 3 b = 12 (1 + i):  12 ((a0 - a1) + (a0 + a1) i)
+SWU_FN void fe2_mul_b3(Fe2& r, const Fe2& a) {
+    Fe2 t, t2, t4, t8;
+    fe_sub(t.c0, a.c0, a.c1);
+    fe_add(t.c1, a.c0, a.c1);
+    fe2_dbl(t2, t);
+    fe2_dbl(t4, t2);
+    fe2_dbl(t8, t4);
+    fe2_add(r, t8, t4);
+}
+
+// complete addition, RCB15 algorithm 7 (a = 0); sums of two products share one reduction per coefficient
+SWU_FN void g2_add(G2p& r, const G2p& p, const G2p& q) {
+    Fe2 A, B, C, D, E, F, bC, bF, A3, t0, t2, X3, Y3, Z3;
+    fe2_mul(A, p.X, q.X);
+    fe2_mul(B, p.Y, q.Y);
+    fe2_mul(C, p.Z, q.Z);
+    fe2_mul2(D, p.X, q.Y, q.X, p.Y, false);
+    fe2_mul2(E, p.Y, q.Z, q.Y, p.Z, false);
+    fe2_mul2(F, p.X, q.Z, q.X, p.Z, false);
+    fe2_mul_b3(bC, C);
+    fe2_mul_b3(bF, F);
+    fe2_dbl(A3, A); fe2_add(A3, A3, A);
+    fe2_sub(t2, B, bC);                                  // B - bC
+    fe2_add(t0, B, bC);                                  // B + bC
+    fe2_mul2(X3, D, t2, E, bF, true);                    // D (B - bC) - E bF
+    fe2_mul2(Y3, t0, t2, A3, bF, false);                 // (B + bC)(B - bC) + 3A bF
+    fe2_mul2(Z3, E, t0, A3, D, false);                   // E (B + bC) + 3A D
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
+// complete doubling, RCB15 algorithm 9 (a = 0)
+SWU_FN void g2_dbl(G2p& r, const G2p& p) {
+    Fe2 YY, ZZ, XY, YZ, bZZ, t, t0, t1, t3, X3, Y3, Z3;
+    fe2_sqr(YY, p.Y);
+    fe2_sqr(ZZ, p.Z);
+    fe2_mul(XY, p.X, p.Y);
+    fe2_mul(YZ, p.Y, p.Z);
+    fe2_mul_b3(bZZ, ZZ);
+    fe2_dbl(t0, bZZ); fe2_add(t0, t0, bZZ); fe2_sub(t, YY, t0);          // YY - 3 bZZ
+    fe2_dbl(t0, XY); fe2_mul(X3, t0, t);                                 // 2 XY (YY - 3 bZZ)
+    fe2_dbl(t0, YY); fe2_dbl(t0, t0);                                    // 4 YY
+    fe2_add(t3, YY, bZZ);
+    fe2_dbl(t1, bZZ);
+    fe2_mul2(Y3, t3, t, t0, t1, false);                                  // (YY + bZZ)(YY - 3 bZZ) + 8 YY bZZ
+    fe2_dbl(t1, YZ); fe2_mul(Z3, t0, t1);                                // 8 YY YZ
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
+// Jacobian doublings (x, y) = (X/Z^2, Y/Z^3) for the long zero runs of |x| (dbl-2009-l, a = 0): four squarings + three
+// products instead of the eight products of the complete doubling.  Valid for every point of an odd-order curve incl.
+// infinity in the form (X, Y, 0) with X^3 = Y^2 != 0 (same construction as vmprog/curves.py: to_jacobian / dbl_jacobian).
+SWU_FN void g2_to_jacobian(G2p& r, const G2p& p) {
+    const bool inf = fe2_is_zero(p.Z);
+    Fe2 zz, x, y, one;
+    fe_set(one.c0, kOne); fe_zero(one.c1);
+    fe2_sqr(zz, p.Z);
+    fe2_mul(x, p.X, p.Z);
+    fe2_mul(y, p.Y, zz);
+    fe2_sel(r.X, inf, one, x);
+    fe2_sel(r.Y, inf, one, y);
+    r.Z = p.Z;
+}
+SWU_FN void g2_from_jacobian(G2p& r, const G2p& p) {
+    Fe2 zz, x, z;
+    fe2_sqr(zz, p.Z);
+    fe2_mul(x, p.X, p.Z);
+    fe2_mul(z, zz, p.Z);
+    r.X = x; r.Y = p.Y; r.Z = z;
+}
+SWU_FN void g2_dbl_jacobian(G2p& r, const G2p& p) {
+    Fe2 A, B, Z3, D, A3, X3, Y3, t, bb;
+    fe2_sqr(A, p.X);
+    fe2_sqr(B, p.Y);
+    fe2_dbl(t, p.Y); fe2_mul(Z3, t, p.Z);
+    fe2_dbl(t, p.X); fe2_dbl(t, t); fe2_mul(D, t, B);                    // 4 X B
+    fe2_dbl(A3, A); fe2_add(A3, A3, A);
+    fe2_sqr(X3, A3); fe2_dbl(t, D); fe2_sub(X3, X3, t);                  // (3A)^2 - 2D
+    fe2_sqr(bb, B); fe2_dbl(bb, bb); fe2_dbl(bb, bb); fe2_dbl(bb, bb);   // 8 B^2
+    fe2_sub(t, D, X3); fe2_mul(Y3, A3, t); fe2_sub(Y3, Y3, bb);
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
+SWU_INL void g2_neg(G2p& r, const G2p& p) { r.X = p.X; fe2_neg(r.Y, p.Y); r.Z = p.Z; }
+
+SWU_FN void g2_psi(G2p& r, const G2p& p) {  // math.ts:1398-1403 on projective coordinates
+    Fe2 c, t;
+    fe2_const(c, kPsiCx); fe2_conj(t, p.X); fe2_mul(r.X, t, c);
+    fe2_const(c, kPsiCy); fe2_conj(t, p.Y); fe2_mul(r.Y, t, c);
+    fe2_conj(t, p.Z); r.Z = t;
+}
+SWU_FN void g2_psi2(G2p& r, const G2p& p) {  // math.ts:1406-1408
+    Fe c;
+    fe_set(c, kPsi2C1);
+    Fe2 t;
+    fe2_mul_fe(t, p.X, c);
+    r.X = t; fe2_neg(r.Y, p.Y); r.Z = p.Z;
+}
+
+// [|x|] P, |x| = 0xd201000000010000 (public): MSB-first double-and-add; complete additions, runs of at least four
+// doublings in Jacobian coordinates
+SWU_FN void g2_mul_x(G2p& r, const G2p& p) {
+    const unsigned long long z = 0xd201000000010000ull;
+    G2p acc = p;
+    int i = 62;
+#pragma unroll 1
+    while (i >= 0) {
+        int run = 1;  // doublings up to and including the next set bit (or the end)
+        while (!((z >> (i - run + 1)) & 1ull) && i - run >= 0) ++run;
+        if (run >= 4) {
+            G2p j;
+            g2_to_jacobian(j, acc);
+#pragma unroll 1
+            for (int k = 0; k < run; ++k) g2_dbl_jacobian(j, j);
+            g2_from_jacobian(acc, j);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < run; ++k) g2_dbl(acc, acc);
+        }
+        if ((z >> (i - run + 1)) & 1ull) g2_add(acc, acc, p);
+        i -= run;
+    }
+    r = acc;
+}
+
+// index.ts:659-672
+SWU_FN void g2_clear_cofactor(G2p& r, const G2p& p) {
+    G2p t1, t2, t3, t;
+    g2_mul_x(t1, p); g2_neg(t1, t1);          // [-x] P   (x < 0: mulCurveX = -[|x|])
+    g2_psi(t2, p);
+    g2_dbl(t, p); g2_psi2(t3, t);
+    g2_neg(t, t2); g2_add(t3, t3, t);
+    g2_add(t2, t1, t2);
+    g2_mul_x(t2, t2); g2_neg(t2, t2);
+    g2_add(t3, t3, t2);
+    g2_neg(t, t1); g2_add(t3, t3, t);
+    g2_neg(t, p); g2_add(r, t3, t);
+}
+
+// add-1998-cmo-2 as coded in math.ts:1008-1024, on E' (two independent SWU outputs: the special cases are unreachable)
+SWU_FN void e1_add(G2p& r, const G2p& p, const G2p& q) {
+    Fe2 U1, U2, V1, V2, U, V, VV, VVV, V2VV, W, UU, A, t0, t1;
+    fe2_mul(U1, q.Y, p.Z);
+    fe2_mul(U2, p.Y, q.Z);
+    fe2_mul(V1, q.X, p.Z);
+    fe2_mul(V2, p.X, q.Z);
+    fe2_sub(U, U1, U2);
+    fe2_sub(V, V1, V2);
+    fe2_sqr(VV, V);
+    fe2_mul(VVV, VV, V);
+    fe2_mul(V2VV, V2, VV);
+    fe2_mul(W, p.Z, q.Z);
+    fe2_sqr(UU, U);
+    fe2_mul(t0, UU, W); fe2_sub(t0, t0, VVV); fe2_dbl(t1, V2VV); fe2_sub(A, t0, t1);
+    fe2_mul(r.X, V, A);
+    fe2_sub(t0, V2VV, A); fe2_mul(t0, U, t0); fe2_mul(t1, VVV, U2); fe2_sub(r.Y, t0, t1);
+    fe2_mul(r.Z, VVV, W);
+}
+
+SWU_FN void iso3_poly(Fe2& r, const uint32_t (*k)[2][12], const Fe2* mono) {
+    Fe2 acc, c, t;
+    fe_zero(acc.c0); fe_zero(acc.c1);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        fe2_const(c, k[j]);
+        if (fe2_is_zero(c)) continue;   // public constants
+        fe2_mul(t, mono[j], c);
+        fe2_add(acc, acc, t);
+    }
+    r = acc;
+}
+
+// isogenyMapG2 (math.ts:1315-1325) on a projective point of E', staying projective on E
+SWU_FN void iso3_map(G2p& r, const G2p& p) {
+    Fe2 mono[4], X2, Z2, XN, XD, YN, YD, YDZ, t;
+    fe2_sqr(X2, p.X);
+    fe2_sqr(Z2, p.Z);
+    fe2_mul(mono[0], X2, p.X);
+    fe2_mul(mono[1], X2, p.Z);
+    fe2_mul(mono[2], p.X, Z2);
+    fe2_mul(mono[3], Z2, p.Z);
+    iso3_poly(XN, kIso3_xnum, mono);
+    iso3_poly(XD, kIso3_xden, mono);
+    iso3_poly(YN, kIso3_ynum, mono);
+    iso3_poly(YD, kIso3_yden, mono);
+    fe2_mul(YDZ, YD, p.Z);
+    fe2_mul(r.X, XN, YDZ);
+    fe2_mul(t, p.Y, YN); fe2_mul(r.Y, t, XD);
+    fe2_mul(r.Z, XD, YDZ);
+}
+
+// (x, y) = (X/Z, Y/Z); Z = 0 gives (0, 0)
+SWU_FN void g2_to_affine(Fe2& x, Fe2& y, const G2p& p) {
+    Fe n, ni;
+    fe_dot2(n, p.Z.c0.v, p.Z.c0.v, p.Z.c1.v, p.Z.c1.v);
+    fpc::fp_inv_mont(ni.v, n.v);
+    Fe2 zi;
+    fe_mul(zi.c0, p.Z.c0, ni);
+    fe_mul(zi.c1, p.Z.c1, ni);
+    fe_neg(zi.c1, zi.c1);
+    fe2_mul(x, p.X, zi);
+    fe2_mul(y, p.Y, zi);
+}
+
+FPC_DEV void fe_load_be(Fe& r, const uint8_t* p) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const uint8_t* q = p + 4 * (11 - k);
+        r.v[k] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+}
+// leave Montgomery form: the canonical plain integer
+SWU_FN void fe_plain(Fe& r, const Fe& a) {
+    Fe one_plain;
+    fe_zero(one_plain);
+    one_plain.v[0] = 1;
+    fe_mul(r, a, one_plain);
+}
+FPC_DEV bool fe_gt_half(const Fe& plain) {  // plain > (p - 1)/2
+    uint32_t t[12];
+    return fpc::sub12(t, fpc::kHalfP, plain.v) != 0;
+}
+
+SWU_FN void load_e1_points(G2p& p0, G2p& p1, const uint8_t* in576) {
+    fe_load_be(p0.X.c0, in576); fe_load_be(p0.X.c1, in576 + 48); fe_load_be(p0.Y.c0, in576 + 96);
+    fe_load_be(p0.Y.c1, in576 + 144); fe_load_be(p0.Z.c0, in576 + 192); fe_load_be(p0.Z.c1, in576 + 240);
+    in576 += 288;
+    fe_load_be(p1.X.c0, in576); fe_load_be(p1.X.c1, in576 + 48); fe_load_be(p1.Y.c0, in576 + 96);
+    fe_load_be(p1.Y.c1, in576 + 144); fe_load_be(p1.Z.c0, in576 + 192); fe_load_be(p1.Z.c1, in576 + 240);
+}
+
+// H(m) as a projective point of G2 from the two SWU outputs
+SWU_FN void hash_tail(G2p& h, const uint8_t* in576) {
+    G2p p0, p1, s, e;
+    load_e1_points(p0, p1, in576);
+    e1_add(s, p0, p1);
+    iso3_map(e, s);
+    g2_clear_cofactor(h, e);
+}
+
+// one message: 576 B (two points of E') -> 192 B affine H(m) (x.c0, x.c1, y.c0, y.c1; plain big-endian)
+SWU_FN void h2g2_tail_one(const uint8_t* in576, uint8_t* out192) {
+    G2p h;
+    hash_tail(h, in576);
+    Fe2 x, y;
+    g2_to_affine(x, y, h);
+    Fe t;
+    fe_plain(t, x.c0); fe_store_be(out192, t);
+    fe_plain(t, x.c1); fe_store_be(out192 + 48, t);
+    fe_plain(t, y.c0); fe_store_be(out192 + 96, t);
+    fe_plain(t, y.c1); fe_store_be(out192 + 144, t);
+}
+
+FPC_DEV void g2_cmov(G2p& r, bool c, const G2p& a) {  // r = c ? a : r, no branch on c
+    fe2_sel(r.X, c, a.X, r.X);
+    fe2_sel(r.Y, c, a.Y, r.Y);
+    fe2_sel(r.Z, c, a.Z, r.Z);
+}
+
+// sign: [k] H(m), k < z^4 given by its four base-z digits a_3 || a_2 || a_1 || a_0 (8 bytes big-endian each, z = |x|).
+// psi(P) = [x]P = -[z]P on G2 (the reference's own subgroup test, index.ts:688-690), so
+//     [k]P = a_0 Q_0 + a_1 Q_1 + a_2 Q_2 + a_3 Q_3,  Q_i = (-1)^i psi^i(P):
+// ONE joint 64-step ladder (double, 16-way constant-time select over the table of subset sums -- every entry is read, no
+// address or branch depends on the scalar -- and one complete addition per step) instead of the 255 double-and-adds of a
+// plain ladder (math.ts:1061-1078).  Same group element, same bytes.  Output: toSignature (index.ts:586-598), 96 bytes.
+SWU_FN void sign_one(const uint8_t* in576, const uint8_t* digits32, uint8_t* out96) {
+    G2p tab[16];
+    {
+        G2p h, q;
+        hash_tail(h, in576);
+        fe_zero(tab[0].X.c0); fe_zero(tab[0].X.c1); fe_set(tab[0].Y.c0, kOne); fe_zero(tab[0].Y.c1); fe_zero(tab[0].Z.c0); fe_zero(tab[0].Z.c1);
+        tab[1] = h;
+        g2_psi(q, h); g2_neg(tab[2], q);                 // Q_1 = -psi(P)
+        g2_psi2(tab[4], h);                              // Q_2 = psi^2(P)
+        g2_psi(q, tab[4]); g2_neg(tab[8], q);            // Q_3 = -psi^3(P)
+#pragma unroll 1
+        for (int b = 1; b < 4; ++b) {
+            const int base = 1 << b;
+#pragma unroll 1
+            for (int k = 1; k < base; ++k) g2_add(tab[base + k], tab[base], tab[k]);
+        }
+    }
+    unsigned long long a[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        unsigned long long v = 0;
+        for (int b = 0; b < 8; ++b) v = (v << 8) | digits32[8 * (3 - d) + b];
+        a[d] = v;
+    }
+    G2p acc, sel;
+#pragma unroll 1
+    for (int j = 63; j >= 0; --j) {
+        const uint32_t idx = (uint32_t)((a[0] >> j) & 1ull) | ((uint32_t)((a[1] >> j) & 1ull) << 1) |
+                             ((uint32_t)((a[2] >> j) & 1ull) << 2) | ((uint32_t)((a[3] >> j) & 1ull) << 3);
+        sel = tab[0];
+#pragma unroll 1
+        for (uint32_t k = 1; k < 16; ++k) g2_cmov(sel, k == idx, tab[k]);
+        if (j == 63) {
+            acc = sel;
+        } else {
+            g2_dbl(acc, acc);
+            g2_add(acc, acc, sel);
+        }
+    }
+    const bool is_inf = fe2_is_zero(acc.Z);
+    Fe2 x, y;
+    g2_to_affine(x, y, acc);
+    // (one temporary on purpose: with four live results of fe_plain the sm_100a build returned the same value for all of
+    // them -- found by the KAT tests, the host build was right; this form is the one h2g2_tail_one uses)
+    Fe t;
+    fe_plain(t, x.c1); fe_store_be(out96, t);
+    fe_plain(t, x.c0); fe_store_be(out96 + 48, t);
+    fe_plain(t, y.c1);
+    const bool y1_zero = fe_is_zero(t), g1 = fe_gt_half(t);
+    fe_plain(t, y.c0);
+    const bool g0 = fe_gt_half(t);
+    const bool aflag = y1_zero ? g0 : g1;   // index.ts:592-596
+    if (is_inf) {
+        for (int k = 0; k < 96; ++k) out96[k] = 0;
+        out96[0] = 0xC0;
+    } else {
+        out96[0] |= 0x80 | (aflag ? 0x20 : 0);
+    }
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(128, 4) h2g2_tail_kernel(const uint8_t* points, uint8_t* out192, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    h2g2_tail_one(points + 576 * i, out192 + 192 * i);
+}
+__global__ void __launch_bounds__(128, 4) sign_kernel(const uint8_t* points, const uint8_t* digits, uint8_t* out96, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sign_one(points + 576 * i, digits + 32 * i, out96 + 96 * i);
+}
+#endif
+
+}  // namespace swu

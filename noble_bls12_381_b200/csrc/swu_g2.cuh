@@ -54,38 +54,65 @@ FPC_DEV void fe_sel(Fe& r, bool c, const Fe& a, const Fe& b) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) r.v[k] = c ? a.v[k] : b.v[k];
 }
-FPC_DEV void fe_add(Fe& r, const Fe& a, const Fe& b) { fpc::add_mod(r.v, a.v, b.v); }
-FPC_DEV void fe_sub(Fe& r, const Fe& a, const Fe& b) {
+// Small functions are calls on purpose: the kernels of this file and of g2_kernels.cuh are long straight-line sequences of
+// field operations, and what decides their speed is whether the hot code stays in the instruction cache (measured: with
+// four inlined multiply-accumulate bodies the tail kernel ran at 43 % of the multiplier, with one at 71 %).
+SWU_FN void fe_add(Fe& r, const Fe& a, const Fe& b) {
+    Fe t;
+    fpc::add_mod(t.v, a.v, b.v);
+    r = t;
+}
+SWU_FN void fe_sub(Fe& r, const Fe& a, const Fe& b) {
     Fe t;
     fpc::sub_mod(t.v, a.v, b.v);
     r = t;
 }
-FPC_DEV void fe_neg(Fe& r, const Fe& a) {
+SWU_INL void fe_neg(Fe& r, const Fe& a) {
     Fe z;
     fe_zero(z);
     fe_sub(r, z, a);
 }
 
-// canonical Montgomery products (operands canonical)
-SWU_FN void fe_mul(Fe& r, const Fe& a, const Fe& b) {
-    Fe t;
-    fpc::mont_mul(t.v, a.v, b.v);
-    r = t;
-}
-// r = a0*b0 + a1*b1 (one reduction); operands < 2p
-SWU_FN void fe_dot2(Fe& r, const uint32_t* a0, const uint32_t* b0, const uint32_t* a1, const uint32_t* b1) {
+// THE multiplier: r = sum_{k < n} x_k * y_k / R mod p, canonical, ONE reduction (n <= 4; every operand <= 2p and the sum of
+// the products below 4p^2, so the reduced value is below 1.41p).  One multiply-accumulate body and one reduction body for
+// all callers.
+SWU_FN void fe_dotn(Fe& r, int n, const uint32_t* const* xs, const uint32_t* const* ys) {
     fpc::Acc A;
     fpc::acc_zero(A);
-    fpc::acc_mac(A, a0, b0);
-    fpc::acc_mac(A, a1, b1);
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        uint32_t x[12], y[12];
+        fpc::copy12(x, xs[k]);
+        fpc::copy12(y, ys[k]);
+        fpc::acc_mac(A, x, y);
+    }
     Fe t;
     fpc::acc_redc(A, t.v);
-    fpc::correct(t.v, 2);
+    fpc::correct(t.v, 1);
     r = t;
 }
+SWU_INL void fe_mul(Fe& r, const Fe& a, const Fe& b) {
+    const uint32_t* xs[1] = {a.v};
+    const uint32_t* ys[1] = {b.v};
+    fe_dotn(r, 1, xs, ys);
+}
+// r = a0*b0 + a1*b1
+SWU_INL void fe_dot2(Fe& r, const uint32_t* a0, const uint32_t* b0, const uint32_t* a1, const uint32_t* b1) {
+    const uint32_t* xs[2] = {a0, a1};
+    const uint32_t* ys[2] = {b0, b1};
+    fe_dotn(r, 2, xs, ys);
+}
 
-FPC_DEV void fe2_add(Fe2& r, const Fe2& a, const Fe2& b) { fe_add(r.c0, a.c0, b.c0); fe_add(r.c1, a.c1, b.c1); }
-FPC_DEV void fe2_neg(Fe2& r, const Fe2& a) { fe_neg(r.c0, a.c0); fe_neg(r.c1, a.c1); }
+// r = x0*y0 + x1*y1 + x2*y2 + x3*y3 (one reduction); operands <= p
+SWU_INL void fe_dot4(Fe& r, const uint32_t* x0, const uint32_t* y0, const uint32_t* x1, const uint32_t* y1, const uint32_t* x2,
+                     const uint32_t* y2, const uint32_t* x3, const uint32_t* y3) {
+    const uint32_t* xs[4] = {x0, x1, x2, x3};
+    const uint32_t* ys[4] = {y0, y1, y2, y3};
+    fe_dotn(r, 4, xs, ys);
+}
+
+SWU_INL void fe2_add(Fe2& r, const Fe2& a, const Fe2& b) { fe_add(r.c0, a.c0, b.c0); fe_add(r.c1, a.c1, b.c1); }
+SWU_INL void fe2_neg(Fe2& r, const Fe2& a) { fe_neg(r.c0, a.c0); fe_neg(r.c1, a.c1); }
 FPC_DEV void fe2_sel(Fe2& r, bool c, const Fe2& a, const Fe2& b) { fe_sel(r.c0, c, a.c0, b.c0); fe_sel(r.c1, c, a.c1, b.c1); }
 FPC_DEV bool fe2_is_zero(const Fe2& a) { return fe_is_zero(a.c0) && fe_is_zero(a.c1); }
 FPC_DEV void fe2_const(Fe2& r, const uint32_t (*k)[12]) { fe_set(r.c0, k[0]); fe_set(r.c1, k[1]); }
@@ -100,36 +127,61 @@ SWU_FN void fe2_mul(Fe2& r, const Fe2& a, const Fe2& b) {
     r.c0 = t0;
     r.c1 = t1;
 }
-SWU_INL void fe2_sqr(Fe2& r, const Fe2& a) { fe2_mul(r, a, a); }
+// r = a b + c d  (sub = false)  or  a b - c d  (sub = true): eight products, ONE reduction per coefficient
+SWU_FN void fe2_mul2(Fe2& r, const Fe2& a, const Fe2& b, const Fe2& c, const Fe2& d, bool sub) {
+    uint32_t na1[12], nc0[12], nc1[12];
+    fpc::neg_raw(na1, a.c1.v);
+    fpc::neg_raw(nc0, c.c0.v);
+    fpc::neg_raw(nc1, c.c1.v);
+    Fe t0, t1;
+    // real: a0 b0 - a1 b1 +- (c0 d0 - c1 d1);   imaginary: a0 b1 + a1 b0 +- (c0 d1 + c1 d0)
+    fe_dot4(t0, a.c0.v, b.c0.v, na1, b.c1.v, sub ? nc0 : c.c0.v, d.c0.v, sub ? c.c1.v : nc1, d.c1.v);
+    fe_dot4(t1, a.c0.v, b.c1.v, a.c1.v, b.c0.v, sub ? nc0 : c.c0.v, d.c1.v, sub ? nc1 : c.c1.v, d.c0.v);
+    r.c0 = t0;
+    r.c1 = t1;
+}
+// (a0 + a1 i)^2 = (a0 + a1)(a0 - a1) + 2 a0 a1 i: two products instead of four   (math.ts:477-484)
+SWU_FN void fe2_sqr(Fe2& r, const Fe2& a) {
+    uint32_t s[12], d[12], n1[12], a2[12];
+    (void)fpc::add12(s, a.c0.v, a.c1.v);        // < 2p
+    fpc::neg_raw(n1, a.c1.v);
+    (void)fpc::add12(d, a.c0.v, n1);            // a0 + (p - a1) <= 2p
+    (void)fpc::add12(a2, a.c0.v, a.c0.v);       // 2 a0 < 2p
+    Fe t0, t1;
+    {
+        const uint32_t* xs[1] = {s};
+        const uint32_t* ys[1] = {d};
+        fe_dotn(t0, 1, xs, ys);
+    }
+    {
+        const uint32_t* xs[1] = {a2};
+        const uint32_t* ys[1] = {a.c1.v};
+        fe_dotn(t1, 1, xs, ys);
+    }
+    r.c0 = t0;
+    r.c1 = t1;
+}
 SWU_INL void fe2_mul_fe(Fe2& r, const Fe2& a, const Fe& k) { fe_mul(r.c0, a.c0, k); fe_mul(r.c1, a.c1, k); }
 
 // a^((p-3)/4): sliding windows over the odd powers; everything but the table look-ups stays in registers
 SWU_FN void fe_pow_p34(Fe& r, const Fe& a) {
     Fe tab[8];
     Fe a2;
-    fpc::mont_mul(a2.v, a.v, a.v);
+    fe_mul(a2, a, a);
     tab[0] = a;
 #pragma unroll 1
-    for (int k = 1; k < 8; ++k) fpc::mont_mul(tab[k].v, tab[k - 1].v, a2.v);
+    for (int k = 1; k < 8; ++k) fe_mul(tab[k], tab[k - 1], a2);
     Fe acc = tab[kPowIdx[0]];
 #pragma unroll 1
-    for (int w = 1; w < kPowWindows; ++w) {
-        const int nsq = kPowSq[w];
+    for (int w = 1; w <= kPowWindows; ++w) {   // the last round only runs the kPowTail squarings
+        const int nsq = w < kPowWindows ? kPowSq[w] : kPowTail;
 #pragma unroll 1
-        for (int s = 0; s < nsq; ++s) {
+        for (int s = 0; s < nsq; ++s) {        // the hot loop: the ONE inlined product of this function, in registers
             Fe t;
             fpc::mont_mul(t.v, acc.v, acc.v);
             acc = t;
         }
-        Fe t;
-        fpc::mont_mul(t.v, acc.v, tab[kPowIdx[w]].v);
-        acc = t;
-    }
-#pragma unroll 1
-    for (int s = 0; s < kPowTail; ++s) {
-        Fe t;
-        fpc::mont_mul(t.v, acc.v, acc.v);
-        acc = t;
+        if (w < kPowWindows) fe_mul(acc, acc, tab[kPowIdx[w]]);
     }
     r = acc;
 }
@@ -167,8 +219,8 @@ SWU_FN bool fe2_sgn0(const Fe2& a) {
     Fe one_plain, x0, x1;
     fe_zero(one_plain);
     one_plain.v[0] = 1;
-    fpc::mont_mul(x0.v, a.c0.v, one_plain.v);
-    fpc::mont_mul(x1.v, a.c1.v, one_plain.v);
+    fe_mul(x0, a.c0, one_plain);
+    fe_mul(x1, a.c1, one_plain);
     const bool s0 = x0.v[0] & 1u, z0 = fe_is_zero(x0), s1 = x1.v[0] & 1u;
     return s0 || (z0 && s1);
 }

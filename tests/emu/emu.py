@@ -13,7 +13,7 @@ def lib():
     if _LIB is None:
         so = os.environ.get("BLS381_EMU_LIB") or os.path.join(HERE, "_build", "libvm_emu.so")
         src = os.path.join(HERE, "vm_emu.cpp")
-        deps = [src] + [os.path.join(ROOT, "noble_bls12_381_b200", "csrc", f) for f in ("vm.cuh", "fp_core.cuh", "fp_core_gen.cuh", "fp_inv.cuh", "swu_g2.cuh", "swu_g2_gen.cuh")]
+        deps = [src] + [os.path.join(ROOT, "noble_bls12_381_b200", "csrc", f) for f in ("vm.cuh", "fp_core.cuh", "fp_core_gen.cuh", "fp_inv.cuh", "swu_g2.cuh", "swu_g2_gen.cuh", "g2_kernels.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             os.makedirs(os.path.dirname(so), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, src])

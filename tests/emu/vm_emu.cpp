@@ -9,6 +9,7 @@
 #include "../../noble_bls12_381_b200/csrc/vm.cuh"
 #include "../../noble_bls12_381_b200/csrc/fp_inv.cuh"
 #include "../../noble_bls12_381_b200/csrc/swu_g2.cuh"
+#include "../../noble_bls12_381_b200/csrc/g2_kernels.cuh"
 
 extern "C" {
 
@@ -29,6 +30,12 @@ void emu_fp_inv(int n, const uint32_t* x, uint32_t* r) { for (int i = 0; i < n; 
 
 // hash_to_field + SWU for G2 (csrc/swu_g2.cuh): n field elements, 128 uniform bytes in, 288 bytes out each
 void emu_swu_g2(const uint8_t* in, uint8_t* out, size_t n) { for (size_t i = 0; i < n; ++i) swu::swu_g2_one(in + 128 * i, out + 288 * i); }
+
+// csrc/g2_kernels.cuh: tail of hash-to-curve (576 B -> 192 B affine) and sign (576 B + 32 B digits -> 96 B signature)
+void emu_h2g2_tail(const uint8_t* in, uint8_t* out, size_t n) { for (size_t i = 0; i < n; ++i) swu::h2g2_tail_one(in + 576 * i, out + 192 * i); }
+void emu_sign_tail(const uint8_t* in, const uint8_t* digits, uint8_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) swu::sign_one(in + 576 * i, digits + 32 * i, out + 96 * i);
+}
 
 void emu_add_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::add_mod(r, a, b); }
 void emu_sub_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::sub_mod(r, a, b); }

@@ -305,6 +305,40 @@ def test_sign_tail_program_against_reference_kats():
         assert bytes(body).hex() == sig.strip().lower(), i
 
 
+def test_tail_kernels_source_against_oracle_and_kats():
+    """csrc/g2_kernels.cuh (host build of the kernels' source): tail of hash-to-curve vs the oracle's hashToCurve, and the
+    sign ladder + toSignature vs the reference's KATs (index.test.ts:287-293) incl. edge scalars vs the oracle."""
+    import ctypes
+    lib = emu.lib()
+    msgs = [b"", b"abc", bytes(range(32)), b"x" * 100, b"abcdef0123456789"]
+    n = len(msgs)
+    pts = _swu_points(b"".join(O.expand_message_xmd(m, O.DEFAULT_DST, 256) for m in msgs))
+    out = (ctypes.c_uint8 * (192 * n))()
+    lib.emu_h2g2_tail(bytes(pts), out, ctypes.c_size_t(n))
+    out = bytes(out)
+    for i, m in enumerate(msgs):
+        (x0, x1), (y0, y1) = O.pt_to_affine(O.G2, O.g2_hash_to_curve(m))
+        assert out[192 * i : 192 * i + 192] == b"".join(v.to_bytes(48, "big") for v in (x0, x1, y0, y1)), i
+    lines = [l.split(":") for l in open(os.path.join(GOLDEN, "sign_g2_vectors.txt")).read().split("\n") if l][12:24]
+    z = 0xD201000000010000
+
+    def digits(k):
+        a = [(k // z**i) % z for i in range(4)]
+        return b"".join(a[i].to_bytes(8, "big") for i in (3, 2, 1, 0))
+
+    cases = [(int(sk, 16) % O.R_ORDER, bytes.fromhex(m), sig.strip().lower()) for sk, m, sig in lines]
+    for k in (1, 2, z - 1, z, z + 1, z * z, z**3 - 1, O.R_ORDER - 1):  # digit patterns with zero / single / full digits
+        m = b"edge%d" % (k % 1000)
+        cases.append((k, m, O.g2_to_signature(O.pt_multiply_unsafe(O.G2, O.g2_hash_to_curve(m), k)).hex()))
+    n = len(cases)
+    pts = _swu_points(b"".join(O.expand_message_xmd(m, O.DEFAULT_DST, 256) for _, m, _ in cases))
+    sig = (ctypes.c_uint8 * (96 * n))()
+    lib.emu_sign_tail(bytes(pts), b"".join(digits(k) for k, _, _ in cases), sig, ctypes.c_size_t(n))
+    sig = bytes(sig)
+    for i, (_, _, want) in enumerate(cases):
+        assert sig[96 * i : 96 * i + 96].hex() == want, i
+
+
 def test_validate_programs_edge_points():
     """assertValidity (index.ts:383-388 / 633-638) through the fixed-scalar multiplication with Jacobian doubling runs:
     subgroup points, on-curve points outside the subgroup, a point of the curve's small-order part (a multiple of r of a
