@@ -59,6 +59,7 @@ struct State {
     int sleep_ns = 0;    // back-off of the dataflow poll loop (env BLS381_B200_SLEEP_NS)
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
     int swu_kernel = 1;  // hash-to-curve front (hash_to_field + SWU) as the hand-written kernel; 0 = all inside the tower-VM program (A/B)
+    int g1_kernel = 1;   // G1 key decompression + subgroup check as a hand-written kernel; 0 = tower-VM program g1_decompress (A/B)
     int tail_kernels = 1;  // tail of hash-to-curve / sign ladder as hand-written kernels (needs swu_kernel); 0 = tower-VM programs h2g2_tail / sign_tail (A/B)
     // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
     // verifyBatch at 131072 signatures on a B200: 1.26 / 1.39 / 1.42 / 1.40 M sigs/s for 1 / 2 / 3 / 4
@@ -457,6 +458,15 @@ int run3(const char* prog, uint8_t* in, uint32_t in_stride, uint8_t* out, uint32
     return vm_run(prog, bufs, strides, 6, n, s);
 }
 
+// PointG1.fromHex (48-byte keys) + assertValidity: n x 48 B -> n x 96 B affine + status   (index.ts:298-327, 383-388)
+int g1_decompress_dev(uint8_t* d_in, uint8_t* d_out, int32_t* d_status, size_t n, cudaStream_t s) {
+    if (!g.g1_kernel) return run3("g1_decompress", d_in, 48, d_out, 96, d_status, n, s);
+    swu::g1_decompress_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_out, d_status, n);
+    CUDA_TRY(cudaGetLastError());
+    g.launches.fetch_add(1);
+    return BLS381_OK;
+}
+
 // g.d_stage[4] (n x 256 uniform bytes) -> g.d_stage[10] (n x 576 B: the two points of E' per message), csrc/swu_g2.cuh
 int swu_points(size_t n, cudaStream_t s) {
     int rc;
@@ -594,6 +604,7 @@ int init_context(int device, const char* program_dir) {   // caller holds g.mu; 
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
     if (const char* e = getenv("BLS381_B200_SWU_KERNEL")) g.swu_kernel = atoi(e);
     if (const char* e = getenv("BLS381_B200_TAIL_KERNELS")) g.tail_kernels = atoi(e);
+    if (const char* e = getenv("BLS381_B200_G1_KERNEL")) g.g1_kernel = atoi(e);
     if (const char* e = getenv("BLS381_B200_PAIRS_PER_LANE")) g.pairs_per_lane = atoi(e);
     if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
     if (const char* e = getenv("BLS381_B200_LOG_LAUNCHES")) g.log_launches = atoi(e);
@@ -741,6 +752,7 @@ int bls381_set_option(const char* name, int value) {
     else if (n == "no_tma") g.no_tma = value != 0;
     else if (n == "swu_kernel") g.swu_kernel = value != 0;
     else if (n == "tail_kernels") g.tail_kernels = value != 0;
+    else if (n == "g1_kernel") g.g1_kernel = value != 0;
     else if (n == "pairs_per_lane") g.pairs_per_lane = value;
     else return fail(BLS381_EINVAL, "unknown option: " + n);
     return BLS381_OK;
@@ -898,7 +910,7 @@ int bls381_g1_decompress_batch(const uint8_t* in48, size_t n, uint8_t* out96, in
     int rc;
     if ((rc = stage(0, n * 48)) || (rc = stage(2, n * 96)) || (rc = stage(6, n * 4))) return rc;
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in48, n * 48, cudaMemcpyHostToDevice, g.stream));
-    if ((rc = run3("g1_decompress", g.d_stage[0], 48, g.d_stage[2], 96, (int32_t*)g.d_stage[6], n, g.stream))) return rc;
+    if ((rc = g1_decompress_dev(g.d_stage[0], g.d_stage[2], (int32_t*)g.d_stage[6], n, g.stream))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out96, g.d_stage[2], n * 96, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -1012,7 +1024,7 @@ static int verify_partial(const uint8_t* sig96, const uint8_t* msgs, const uint6
     }
     if (n) {
         // publicKeys.map(normP1)  (index.ts:801)
-        if ((rc = run3("g1_decompress", g.d_stage[7], 48, d_g1, 96, d_st, n, s))) return rc;
+        if ((rc = g1_decompress_dev(g.d_stage[7], d_g1, d_st, n, s))) return rc;
         // messages.map(normP2Hash)  (index.ts:800)
         if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, d_g2, s))) return rc;
     }
@@ -1434,7 +1446,9 @@ static int aggregate_host(bool g2, const uint8_t* in, size_t n, uint8_t* out, in
     cudaStream_t s = g.stream;
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * cb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(g.ev0, s));
-    if ((rc = run3(g2 ? "g2_decompress" : "g1_decompress", g.d_stage[0], cb, g.d_stage[8], 2 * cb, (int32_t*)g.d_stage[6], n, s))) return rc;
+    if ((rc = g2 ? run3("g2_decompress", g.d_stage[0], cb, g.d_stage[8], 2 * cb, (int32_t*)g.d_stage[6], n, s)
+                 : g1_decompress_dev(g.d_stage[0], g.d_stage[8], (int32_t*)g.d_stage[6], n, s)))
+        return rc;
     if ((rc = aggregate_dev(g2, g.d_stage[8], (int32_t*)g.d_stage[6], n, g.d_stage[9], s))) return rc;
     CUDA_TRY(cudaEventRecord(g.ev1, s));
     CUDA_TRY(cudaMemcpyAsync(out, g.d_stage[9], cb, cudaMemcpyDeviceToHost, s));

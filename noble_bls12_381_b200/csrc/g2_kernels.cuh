@@ -363,3 +363,123 @@ __global__ void __launch_bounds__(128, 4) sign_kernel(const uint8_t* points, con
 #endif
 
 }  // namespace swu
+
+// ---- G1: PointG1.fromHex for 48-byte compressed keys incl. assertValidity (index.ts:298-327, 383-388) ----------------
+// Same decisions as the tower-VM program g1_decompress (vmprog/curves.py: build_g1_decompress): x from the low 381 bits
+// (reduced mod p like `new Fp`), y = (x^3 + 4)^((p+1)/4) with the sign rule of index.ts:313-314, the subgroup test
+// [z]([z]P) == phi(P) of index.ts:444-448 (z = |x|, phi: x -> beta x) with complete projective formulas.
+namespace swu {
+
+struct G1p { Fe X, Y, Z; };
+
+SWU_FN void fe_mul12(Fe& r, const Fe& a) {  // 3 b = 12
+    Fe t2, t4, t8;
+    fe_add(t2, a, a);
+    fe_add(t4, t2, t2);
+    fe_add(t8, t4, t4);
+    fe_add(r, t8, t4);
+}
+
+// complete addition, RCB15 algorithm 7 (a = 0)
+SWU_FN void g1_add(G1p& r, const G1p& p, const G1p& q) {
+    Fe A, B, C, D, E, F, bC, bF, A3, t0, t2, X3, Y3, Z3;
+    uint32_t nE[12];
+    fe_mul(A, p.X, q.X);
+    fe_mul(B, p.Y, q.Y);
+    fe_mul(C, p.Z, q.Z);
+    fe_dot2(D, p.X.v, q.Y.v, q.X.v, p.Y.v);
+    fe_dot2(E, p.Y.v, q.Z.v, q.Y.v, p.Z.v);
+    fe_dot2(F, p.X.v, q.Z.v, q.X.v, p.Z.v);
+    fe_mul12(bC, C);
+    fe_mul12(bF, F);
+    fe_add(A3, A, A); fe_add(A3, A3, A);
+    fe_sub(t2, B, bC);
+    fe_add(t0, B, bC);
+    fpc::neg_raw(nE, E.v);
+    fe_dot2(X3, D.v, t2.v, nE, bF.v);            // D (B - bC) - E bF
+    fe_dot2(Y3, t0.v, t2.v, A3.v, bF.v);         // (B + bC)(B - bC) + 3A bF
+    fe_dot2(Z3, E.v, t0.v, A3.v, D.v);           // E (B + bC) + 3A D
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
+// complete doubling, RCB15 algorithm 9 (a = 0)
+SWU_FN void g1_dbl(G1p& r, const G1p& p) {
+    Fe YY, ZZ, XY, YZ, bZZ, t, t0, t1, t3, X3, Y3, Z3;
+    fe_mul(YY, p.Y, p.Y);
+    fe_mul(ZZ, p.Z, p.Z);
+    fe_mul(XY, p.X, p.Y);
+    fe_mul(YZ, p.Y, p.Z);
+    fe_mul12(bZZ, ZZ);
+    fe_add(t0, bZZ, bZZ); fe_add(t0, t0, bZZ); fe_sub(t, YY, t0);     // YY - 3 bZZ
+    fe_add(t0, XY, XY); fe_mul(X3, t0, t);
+    fe_add(t0, YY, YY); fe_add(t0, t0, t0);                           // 4 YY
+    fe_add(t3, YY, bZZ);
+    fe_add(t1, bZZ, bZZ);
+    fe_dot2(Y3, t3.v, t.v, t0.v, t1.v);                               // (YY + bZZ)(YY - 3 bZZ) + 8 YY bZZ
+    fe_add(t1, YZ, YZ); fe_mul(Z3, t0, t1);                           // 8 YY YZ
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
+SWU_FN void g1_mul_x(G1p& r, const G1p& p) {  // [|x|] P
+    const unsigned long long z = 0xd201000000010000ull;
+    G1p acc = p;
+#pragma unroll 1
+    for (int i = 62; i >= 0; --i) {
+        g1_dbl(acc, acc);
+        if ((z >> i) & 1ull) g1_add(acc, acc, p);
+    }
+    r = acc;
+}
+
+// index.ts:444-448
+SWU_FN bool g1_is_torsion_free(const G1p& p) {
+    G1p xP, u2P;
+    g1_mul_x(xP, p);
+    fe_neg(xP.Y, xP.Y);                       // mulCurveX = -[z] P
+    g1_mul_x(u2P, xP);
+    Fe beta, px, l, rr;
+    fe_set(beta, kCubicRoot);
+    fe_mul(px, p.X, beta);                    // phi(P) = (beta x, y, z)
+    fe_mul(l, u2P.X, p.Z); fe_mul(rr, px, u2P.Z);
+    const bool xe = fe_eq(l, rr);
+    fe_mul(l, u2P.Y, p.Z); fe_mul(rr, p.Y, u2P.Z);
+    return xe && fe_eq(l, rr);
+}
+
+// one key: 48 B compressed -> 96 B affine (x || y, plain big-endian) + status
+SWU_FN void g1_decompress_one(const uint8_t* in48, uint8_t* out96, int32_t* status) {
+    const bool flag_inf = (in48[0] >> 6) & 1, flag_sign = (in48[0] >> 5) & 1;
+    Fe xr, x, c, right, cand, t;
+    fe_load_be(xr, in48);
+    xr.v[11] &= 0x1FFFFFFFu;                  // the low 381 bits
+    fe_set(c, kR2);
+    fe_mul(x, xr, c);                         // x mod p, Montgomery form (xr < 2^381 < 2p)
+    fe_mul(t, x, x);
+    fe_mul(right, t, x);
+    fe_set(c, kFour);
+    fe_add(right, right, c);                  // x^3 + 4
+    fe_pow_p34(t, right);
+    fe_mul(cand, t, right);                   // right^((p+1)/4)      math.ts:260-264
+    fe_mul(t, cand, cand);
+    const bool no_sqrt = !fe_eq(t, right);
+    Fe plain, y, ny;
+    fe_plain(plain, cand);
+    fe_neg(ny, cand);
+    fe_sel(y, fe_gt_half(plain) != flag_sign, ny, cand);   // (y * 2) / P != aflag  -> negate   (index.ts:313-314)
+    G1p pt;
+    pt.X = x; pt.Y = y; fe_set(pt.Z, kOne);
+    const bool not_sub = !g1_is_torsion_free(pt);
+    fe_plain(plain, x); fe_store_be(out96, plain);
+    fe_plain(plain, y); fe_store_be(out96 + 48, plain);
+    *status = flag_inf ? 1 : (no_sqrt ? 4 : (not_sub ? 3 : 0));   // BLS381_ST_INFINITY / BAD_ENCODING / NOT_IN_SUBGROUP / OK
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(128, 4) g1_decompress_kernel(const uint8_t* in48, uint8_t* out96, int32_t* status, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_decompress_one(in48 + 48 * i, out96 + 96 * i, status + i);
+}
+#endif
+
+}  // namespace swu

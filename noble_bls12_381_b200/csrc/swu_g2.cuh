@@ -33,6 +33,15 @@ namespace swu {
 #define SWU_INL static inline
 #endif
 
+#if !defined(__CUDACC__)
+// host build only (tests/emu): how many 384-bit products / Montgomery reductions one call executes -- bench.py's issued
+// multiply count of these kernels is pinned to these counters by tests/test_vm_ingest_emu.py
+static long g_products = 0, g_reductions = 0;
+#define SWU_COUNT(p, r) do { g_products += (p); g_reductions += (r); } while (0)
+#else
+#define SWU_COUNT(p, r) do { } while (0)
+#endif
+
 struct Fe { uint32_t v[12]; };
 struct Fe2 { Fe c0, c1; };
 
@@ -90,6 +99,7 @@ SWU_FN void fe_dotn(Fe& r, int n, const uint32_t* const* xs, const uint32_t* con
     fpc::acc_redc(A, t.v);
     fpc::correct(t.v, 1);
     r = t;
+    SWU_COUNT(n, 1);
 }
 SWU_INL void fe_mul(Fe& r, const Fe& a, const Fe& b) {
     const uint32_t* xs[1] = {a.v};
@@ -180,6 +190,7 @@ SWU_FN void fe_pow_p34(Fe& r, const Fe& a) {
             Fe t;
             fpc::mont_mul(t.v, acc.v, acc.v);
             acc = t;
+            SWU_COUNT(1, 1);
         }
         if (w < kPowWindows) fe_mul(acc, acc, tab[kPowIdx[w]]);
     }

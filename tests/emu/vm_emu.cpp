@@ -37,6 +37,12 @@ void emu_sign_tail(const uint8_t* in, const uint8_t* digits, uint8_t* out, size_
     for (size_t i = 0; i < n; ++i) swu::sign_one(in + 576 * i, digits + 32 * i, out + 96 * i);
 }
 
+void emu_g1_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
+    for (size_t i = 0; i < n; ++i) swu::g1_decompress_one(in + 48 * i, out + 96 * i, st + i);
+}
+// products / reductions executed by the swu / g2 kernels' source since the last call (host-build counters)
+void emu_swu_counters(long* out2) { out2[0] = swu::g_products; out2[1] = swu::g_reductions; swu::g_products = swu::g_reductions = 0; }
+
 void emu_add_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::add_mod(r, a, b); }
 void emu_sub_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) { fpc::sub_mod(r, a, b); }
 

@@ -143,6 +143,23 @@ def test_g1_decompress_program():
             assert bytes(out[96 * i : 96 * i + 96]) == exp, i
 
 
+def test_g1_decompress_kernel_source():
+    """csrc/g2_kernels.cuh g1_decompress_one (host build of the kernel's source) on the same cases as the tower-VM program:
+    zkcrypto vectors, infinity, no square root, outside the subgroup, non-canonical encodings."""
+    import ctypes
+    items = _g1_cases()
+    n = len(items)
+    out = (ctypes.c_uint8 * (96 * n))()
+    st = (ctypes.c_int32 * n)()
+    emu.lib().emu_g1_decompress(b"".join(items), out, st, ctypes.c_size_t(n))
+    out = bytes(out)
+    for i, it in enumerate(items):
+        exp_st, exp = g1_expected(it)
+        assert st[i] == exp_st, i
+        if exp is not None:
+            assert out[96 * i : 96 * i + 96] == exp, i
+
+
 def test_g2_decompress_program():
     b = vmcompile.compile_program("g2_decompress")
     items = _g2_cases()
@@ -337,6 +354,28 @@ def test_tail_kernels_source_against_oracle_and_kats():
     sig = bytes(sig)
     for i, (_, _, want) in enumerate(cases):
         assert sig[96 * i : 96 * i + 96].hex() == want, i
+
+
+def test_kernel_multiply_counts_used_by_the_bench():
+    """bench.py's issued-multiply figures of the hand-written kernels are the counters of the host build of their source."""
+    import ctypes
+    import bench
+    lib = emu.lib()
+    c = (ctypes.c_long * 2)()
+    uni = O.expand_message_xmd(b"count me", O.DEFAULT_DST, 256)
+    pts = (ctypes.c_uint8 * 576)()
+    out = (ctypes.c_uint8 * 192)()
+    sig = (ctypes.c_uint8 * 96)()
+    lib.emu_swu_counters(c)
+    lib.emu_swu_g2(uni, pts, ctypes.c_size_t(2))
+    lib.emu_swu_counters(c)
+    assert (c[0], c[1]) == bench.KERNEL_COUNTS["swu_g2_kernel"]
+    lib.emu_h2g2_tail(pts, out, ctypes.c_size_t(1))
+    lib.emu_swu_counters(c)
+    assert (c[0], c[1]) == bench.KERNEL_COUNTS["h2g2_tail_kernel"]
+    lib.emu_sign_tail(pts, bytes(31) + b"\x05", sig, ctypes.c_size_t(1))
+    lib.emu_swu_counters(c)
+    assert (c[0], c[1]) == bench.KERNEL_COUNTS["sign_kernel"]
 
 
 def test_validate_programs_edge_points():
