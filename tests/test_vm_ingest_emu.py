@@ -376,6 +376,11 @@ def test_kernel_multiply_counts_used_by_the_bench():
     lib.emu_sign_tail(pts, bytes(31) + b"\x05", sig, ctypes.c_size_t(1))
     lib.emu_swu_counters(c)
     assert (c[0], c[1]) == bench.KERNEL_COUNTS["sign_kernel"]
+    g1c = open(os.path.join(GOLDEN, "zkcrypto_g1_compressed.dat"), "rb").read()
+    o96, st = (ctypes.c_uint8 * 96)(), (ctypes.c_int32 * 1)()
+    lib.emu_g1_decompress(g1c[48:96], o96, st, ctypes.c_size_t(1))
+    lib.emu_swu_counters(c)
+    assert (c[0], c[1]) == bench.KERNEL_COUNTS["g1_decompress_kernel"]
 
 
 def test_validate_programs_edge_points():
