@@ -194,11 +194,13 @@ int bls381_vm_load(const char* name, const uint8_t* image, size_t len);
 /* Engine tuning knobs (same as the BLS381_B200_* environment variables read by bls381_init): "dynamic_batches" (1 = CTAs
  * claim 32-item batches from a global counter, 0 = round-robin), "ctas_per_sm" (0 = automatic), "poll_sleep_ns",
  * "no_tma" (1 = read wire-format inputs directly from global memory), "pairs_per_lane" (1..4, default 3: the
- * Miller-product entry points give every lane that many consecutive items, which share the Fp12 squarings).
- * Results never depend on them.                                                                                 */
+ * Miller-product entry points give every lane that many consecutive items, which share the Fp12 squarings),
+ * "swu_kernel" / "tail_kernels" / "g1_kernel" (default 1: hash_to_field + SWU, the tail of hash-to-curve and the sign
+ * ladder, and G1 key decompression run as hand-written per-item kernels; 0 = the tower-VM programs of the same functions,
+ * kept as the A/B path).  Results never depend on them.                                                          */
 int bls381_set_option(const char* name, int value);
 
-/* Measurement aids (bench.py): number of tower-VM kernel launches since init, and a dependent-free
+/* Measurement aids (bench.py): number of kernel launches (tower-VM and per-item kernels) since init, and a dependent-free
  * IMAD.WIDE.U32 issue-rate microbenchmark (returns multiply-adds per second on the whole device). */
 uint64_t bls381_launch_count(void);
 int bls381_imad_peak(double* imad_per_second);
