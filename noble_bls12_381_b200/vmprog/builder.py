@@ -489,60 +489,68 @@ class Builder:
         g = 0
         for k, _, _ in norm:
             g = math.gcd(g, abs(k))
-        post = 1
-        for cand in (4, 3, 2):
-            if g and g % cand == 0:
-                post = cand
-                break
-        terms = []
-        for k, x, y in norm:
-            k //= post
-            if k < 0:
-                x, k = -x, -k
-            while k > 0:
-                # fold as much of the remaining integer factor as the 4-bit operand coefficients allow
-                fx = 4 // max(abs(c) for c in x.t.values())
-                fy = 4 // max(abs(c) for c in y.t.values())
-                best = None
-                for dx in range(1, fx + 1):
-                    for dy in range(1, fy + 1):
-                        if dx * dy <= k and (best is None or dx * dy > best[0] * best[1]):
-                            best = (dx, dy)
-                dx, dy = best
-                terms.append((x.scale(dx), y.scale(dy)))
-                k -= dx * dy
-        # merge identical (x, y) operand pairs?  (rare; skip)
-        # epilogue: split the Lin into chunks of <= 2 same-kind terms with bound <= 4
         epi_chunks = self._chunk_lin(q.lin)
-        # greedy packing into micro-ops under T<=12, E<=2, bound limits
-        pending_terms = list(terms)
-        pending_epi = list(epi_chunks)
-        partial: list[Val] = []
-        while True:
-            cur_t, cur_e = [], []
-            sumb, kb = 0.0, 0.0
-            while pending_terms and len(cur_t) < MAX_TERMS:
-                x, y = pending_terms[0]
-                b = x.bound() * y.bound()
-                if sumb + b > MAX_SUM_BOUND or post * ((sumb + b) * P_OVER_R + 1) + kb > MAX_K - 0.01:
-                    break
-                cur_t.append(pending_terms.pop(0))
-                sumb += b
-            base = post * (sumb * P_OVER_R + 1) if cur_t else 0.0
-            while pending_epi and len(cur_e) < 2:
-                b = pending_epi[0].bound()
-                if base + kb + b > MAX_K - 0.01:
-                    break
-                cur_e.append(pending_epi.pop(0))
-                kb += b
-            assert cur_t or cur_e, "cannot make progress materialising expression"
-            done = not pending_terms and not pending_epi
-            if done and not partial:
-                return self._emit(cur_t, cur_e, base + kb, post)
-            partial.append(self._emit(cur_t, cur_e, base + kb, post))
-            if done:
-                break
-            # fold partial results into the epilogue queue
+
+        def terms_for(post):
+            terms = []
+            for k, x, y in norm:
+                k //= post
+                if k < 0:
+                    x, k = -x, -k
+                while k > 0:
+                    # fold as much of the remaining integer factor as the 4-bit operand coefficients allow
+                    fx = 4 // max(abs(c) for c in x.t.values())
+                    fy = 4 // max(abs(c) for c in y.t.values())
+                    best = None
+                    for dx in range(1, fx + 1):
+                        for dy in range(1, fy + 1):
+                            if dx * dy <= k and (best is None or dx * dy > best[0] * best[1]):
+                                best = (dx, dy)
+                    dx, dy = best
+                    terms.append((x.scale(dx), y.scale(dy)))
+                    k -= dx * dy
+            return terms
+
+        def pack(terms, post):
+            """greedy packing into micro-ops under T<=12, E<=2, bound limits: [(terms, epilogue chunks, bound)]"""
+            pending_terms = list(terms)
+            pending_epi = list(epi_chunks)
+            plan = []
+            while True:
+                cur_t, cur_e = [], []
+                sumb, kb = 0.0, 0.0
+                while pending_terms and len(cur_t) < MAX_TERMS:
+                    x, y = pending_terms[0]
+                    b = x.bound() * y.bound()
+                    if sumb + b > MAX_SUM_BOUND or post * ((sumb + b) * P_OVER_R + 1) + kb > MAX_K - 0.01:
+                        break
+                    cur_t.append(pending_terms.pop(0))
+                    sumb += b
+                base = post * (sumb * P_OVER_R + 1) if cur_t else 0.0
+                while pending_epi and len(cur_e) < 2:
+                    b = pending_epi[0].bound()
+                    if base + kb + b > MAX_K - 0.01:
+                        break
+                    cur_e.append(pending_epi.pop(0))
+                    kb += b
+                assert cur_t or cur_e, "cannot make progress materialising expression"
+                plan.append((cur_t, cur_e, base + kb))
+                if not pending_terms and not pending_epi:
+                    return plan
+
+        # the common factor is applied as a post-scale of 4, 3 or 2 (first that divides g) -- unless the scaled result
+        # bound then forces the sum to be split over several records and a smaller post-scale (more of the factor folded
+        # into the operands) does it in fewer
+        cands = [c for c in (4, 3, 2) if g and g % c == 0][:1] + [1]
+        post, plan = None, None
+        for cand in cands:
+            pl = pack(terms_for(cand), cand)
+            if plan is None or len(pl) < len(plan):
+                post, plan = cand, pl
+        if len(plan) == 1:
+            cur_t, cur_e, kb = plan[0]
+            return self._emit(cur_t, cur_e, kb, post)
+        partial = [self._emit(cur_t, cur_e, kb, post) for cur_t, cur_e, kb in plan]
         # sum the partial results
         return self.mat(sum((Lin.of(v) for v in partial[1:]), Lin.of(partial[0])))
 

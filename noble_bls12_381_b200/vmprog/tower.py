@@ -198,6 +198,11 @@ class E6:
         return E6(self.c0.m(b), self.c1.m(b), self.c2.m(b))
 
 
+FOLD_T2 = __import__("os").environ.get("BLS381_VM_FOLDT2", "1") != "0"  # 12 xi Rz^2 of the doubling step in one record pair
+SCALED_MILLER = __import__("os").environ.get("BLS381_VM_SCALED", "1") != "0"  # 4R doubling step inside `pairing`
+SYMMETRIC_SQR = __import__("os").environ.get("BLS381_VM_SYMSQR", "1") != "0"  # Fp12 squarings of the Miller loop
+
+
 class E12:
     """Fp12 = Fp6[w]/(w^2 - v)  (math.ts:705)."""
 
@@ -211,7 +216,14 @@ class E12:
 
     def sqr(self):  # (a0 + a1 w)^2 = a0^2 + v a1^2 + 2 a0 a1 w      (math.ts:783-791)
         a0, a1 = self.c0, self.c1
-        return E12(a0.sqr() + a1.mul_v() * a1, a0.scale(2) * a1)
+        if not SYMMETRIC_SQR:
+            return E12(a0.sqr() + a1.mul_v() * a1, a0.scale(2) * a1)
+        # v a1^2 written as a symmetric square (22 Fp products instead of the 36 of a general Fp6 product):
+        # a1^2 = (s0, s1, s2) as in E6.sqr, v (s0, s1, s2) = (xi s2, s0, s1), xi applied to an operand
+        b0, b1, b2 = a1.c0, a1.c1, a1.c2
+        xb2 = b2.mul_xi()
+        va1sq = E6(b0.scale(2) * xb2 + b1 * b1.mul_xi(), b0.sqr() + b1.scale(2) * xb2, b0.scale(2) * b1 + xb2 * b2)
+        return E12(a0.sqr() + va1sq, a0.scale(2) * a1)
 
     def conj(self):  # math.ts:799-801
         return E12(self.c0, -self.c1)
@@ -372,14 +384,19 @@ class Tower:
         return (((t2_t5_pow_q2 * t4_t1_pow_q3).m(b) * t6_t1c_pow_q1).m(b) * t7_t3c_t1).m(b)
 
     # ---- Miller loop with fused line evaluation (math.ts:1331-1388) --------------------------------
-    def miller_loop(self, Px: Lin, Py: Lin, Qx: E2, Qy: E2) -> E12:
-        return self.miller_loop_multi([(Px, Py, Qx, Qy)])
+    def miller_loop(self, Px: Lin, Py: Lin, Qx: E2, Qy: E2, scaled=False) -> E12:
+        return self.miller_loop_multi([(Px, Py, Qx, Qy)], scaled)
 
-    def miller_loop_multi(self, pairs) -> E12:
+    def miller_loop_multi(self, pairs, scaled=False) -> E12:
         """prod_k millerLoop(P_k, Q_k) for the pairs [(Px, Py, Qx, Qy), ...] held by ONE lane, with the Fp12 squaring of
         every iteration shared by all pairs:  f <- f^2 * l_1 * l_2 * ...  Because (f_a f_b)^2 l_a l_b = (f_a^2 l_a)(f_b^2 l_b),
         the result is exactly the product of the individual Miller loops (math.ts:1373-1388 each, conjugated) -- the
-        same canonical bytes as index.ts:815's product, with one squaring per bit instead of one per pair."""
+        same canonical bytes as index.ts:815's product, with one squaring per bit instead of one per pair.
+
+        scaled=True (only where the final exponentiation follows in the same program): the doubling step keeps 4R instead
+        of R (no multiplications by 1/2, math.ts:1349-1350).  Every formula below is homogeneous in (Rx, Ry, Rz), so each
+        line picks up a power of 4: the Miller value changes by a factor in Fp*, which the (p^6 - 1) part of the final
+        exponentiation maps to one -- pairing(P, Q) keeps its bytes, pairing(P, Q, false) must not use this form."""
         b = self.b
         inv2 = self.fp_const(pow(2, -1, P))
         c12 = self.fp_const(12)
@@ -399,19 +416,30 @@ class Tower:
                 Rx, Ry, Rz = R[k]
                 # ---- doubling step (math.ts:1339-1351)
                 t0 = Ry.sqr().m(b)
-                t1 = Rz.sqr().m(b)
+                if not FOLD_T2:
+                    t1 = Rz.sqr().m(b)
                 t4 = (Ry.scale(2) * Rz).m(b)  # (Ry+Rz)^2 - t1 - t0
                 rx2 = Rx.sqr().m(b)
                 rxry = (Rx * Ry).m(b)
-                t2 = (t1.mul_xi() * c12).m(b)  # 3 * t1 * 4(1+u)
-                g = ((t0 - t2.scale(3)) * inv2).m(b)  # (t0 - t3)/2
-                h = ((t0 + t2.scale(3)) * inv2).m(b)  # (t0 + t3)/2
+                if FOLD_T2:
+                    t2 = Rz.sqr().mul_xi().scale(12).m(b)  # 3 * Rz^2 * 4(1+u) as ONE pair of records
+                else:
+                    t2 = (t1.mul_xi() * c12).m(b)  # 3 * t1 * 4(1+u)
                 o0 = t2 - t0
                 o1 = (rx2.scale(3) * Px).m(b)
                 o4 = ((-t4) * Py).m(b)
-                Rx = (g * rxry).m(b)
-                Ry = (h.sqr() - t2.sqr().scale(3)).m(b)
-                Rz = (t0 * t4).m(b)
+                if scaled:
+                    g2 = t0 - t2.scale(3)  # 2 (t0 - t3)/2, used as a two-slot operand
+                    h2 = (t0 + t2.scale(3)).m(b)  # linear record, no product
+                    Rx = (g2 * rxry).scale(2).m(b)
+                    Ry = (h2.sqr() - t2.sqr().scale(12)).m(b)
+                    Rz = (t0 * t4).scale(4).m(b)
+                else:
+                    g = ((t0 - t2.scale(3)) * inv2).m(b)  # (t0 - t3)/2
+                    h = ((t0 + t2.scale(3)) * inv2).m(b)  # (t0 + t3)/2
+                    Rx = (g * rxry).m(b)
+                    Ry = (h.sqr() - t2.sqr().scale(3)).m(b)
+                    Rz = (t0 * t4).m(b)
                 f = line_mul(f, o0, o1, o4)
                 if (X_PARAM >> i) & 1:
                     # ---- addition step (math.ts:1354-1367)
@@ -466,7 +494,7 @@ def build_pairing(warps=6, with_final_exp=True) -> Builder:
     b = Builder(warps)
     t = Tower(b)
     Px, Py, Qx, Qy = _load_g1_g2(b)
-    f = t.miller_loop(Px, Py, Qx, Qy)
+    f = t.miller_loop(Px, Py, Qx, Qy, scaled=with_final_exp and SCALED_MILLER)
     if with_final_exp:
         f = t.final_exponentiate(f)
     _store_f12(b, f)
