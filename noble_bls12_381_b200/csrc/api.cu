@@ -910,10 +910,15 @@ int bls381_g1_decompress_batch(const uint8_t* in48, size_t n, uint8_t* out96, in
     int rc;
     if ((rc = stage(0, n * 48)) || (rc = stage(2, n * 96)) || (rc = stage(6, n * 4))) return rc;
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in48, n * 48, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
     if ((rc = g1_decompress_dev(g.d_stage[0], g.d_stage[2], (int32_t*)g.d_stage[6], n, g.stream))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
     CUDA_TRY(cudaMemcpyAsync(out96, g.d_stage[2], n * 96, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
     return BLS381_OK;
 }
 
@@ -945,9 +950,14 @@ int bls381_hash_to_g2_batch(const uint8_t* msgs, const uint64_t* msg_off, size_t
     if ((rc = stage(0, mbytes + 16)) || (rc = stage(1, (n + 1) * 8)) || (rc = stage(2, n * 192))) return rc;
     if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
     if ((rc = hash_to_g2_dev(g.d_stage[0], (const uint64_t*)g.d_stage[1], n, dst, dst_len, g.d_stage[2], g.stream))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
     CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    g.last_ms = ms;
     return BLS381_OK;
 }
 
