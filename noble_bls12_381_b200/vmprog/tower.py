@@ -200,6 +200,7 @@ class E6:
 
 FOLD_T2 = __import__("os").environ.get("BLS381_VM_FOLDT2", "1") != "0"  # 12 xi Rz^2 of the doubling step in one record pair
 SCALED_MILLER = __import__("os").environ.get("BLS381_VM_SCALED", "1") != "0"  # 4R doubling step inside `pairing`
+EASY_PART_SQR = __import__("os").environ.get("BLS381_VM_EASYSQR", "1") != "0"  # f^(p^6 - 1) as conj(f)^2 / norm
 SYMMETRIC_SQR = __import__("os").environ.get("BLS381_VM_SYMSQR", "1") != "0"  # Fp12 squarings of the Miller loop
 
 
@@ -306,6 +307,13 @@ class Tower:
         k = self.frob12[power % 12]
         return E12(r0, E6(self.mul_const2(t.c0, k), self.mul_const2(t.c1, k), self.mul_const2(t.c2, k))).m(self.b)
 
+    def mul12(self, x: E12, y: E12) -> E12:
+        """dense Fp12 product of materialised operands, materialised"""
+        # (the reference's Karatsuba step over Fp6 on reduced intermediates -- 108 products in 18 records + linear records
+        # instead of 144 in 12 -- was costed with the scheduler's model: same total cost, makespan -0.9 %, three times the
+        # far slots; not used)
+        return (x * y).m(self.b)
+
     # ---- cyclotomic square (math.ts:811-843) -----------------------------------------------------
     @staticmethod
     def _fp4_square(a: E2, b: E2):
@@ -331,7 +339,7 @@ class Tower:
         for i in range(X_PARAM.bit_length() - 2, -1, -1):
             z = self.cyclotomic_square(z).m(b)
             if (X_PARAM >> i) & 1:
-                z = (z * f).m(b)
+                z = self.mul12(z, f)
         return z
 
     # ---- inversion -------------------------------------------------------------------------------
@@ -369,19 +377,27 @@ class Tower:
                 return self.final_exponentiate(f)
         b = self.b
         f = f.m(b)
-        t0 = (self.frob12_map(f, 6) * self.fp12_inv(f).m(b)).m(b)  # f^(p^6) / f
+        if EASY_PART_SQR:
+            # f^(p^6) / f = conj(f) * conj(f) / (f conj(f)) = conj(f)^2 / N,  N = a0^2 - v a1^2 in Fp6 (math.ts:793-797):
+            # one Fp12 squaring and one Fp12-by-Fp6 product (148 Fp products) instead of the inverse and a full Fp12
+            # product (216); the squaring does not wait for the inversion
+            ninv = self.fp6_inv((f.c0.sqr() - f.c1.mul_v() * f.c1).m(b)).m(b)
+            cf2 = f.conj().sqr().m(b)
+            t0 = E12(cf2.c0 * ninv, cf2.c1 * ninv).m(b)
+        else:
+            t0 = (self.frob12_map(f, 6) * self.fp12_inv(f).m(b)).m(b)  # f^(p^6) / f
         t1 = (self.frob12_map(t0, 2) * t0).m(b)
         t2 = self.cyclotomic_exp(t1).conj()
-        t3 = (self.cyclotomic_square(t1).m(b).conj() * t2).m(b)
+        t3 = self.mul12(self.cyclotomic_square(t1).m(b).conj(), t2)
         t4 = self.cyclotomic_exp(t3).conj()
         t5 = self.cyclotomic_exp(t4).conj()
-        t6 = (self.cyclotomic_exp(t5).conj() * self.cyclotomic_square(t2).m(b)).m(b)
+        t6 = self.mul12(self.cyclotomic_exp(t5).conj(), self.cyclotomic_square(t2).m(b))
         t7 = self.cyclotomic_exp(t6).conj()
-        t2_t5_pow_q2 = self.frob12_map((t2 * t5).m(b), 2)
-        t4_t1_pow_q3 = self.frob12_map((t4 * t1).m(b), 3)
-        t6_t1c_pow_q1 = self.frob12_map((t6 * t1.conj()).m(b), 1)
-        t7_t3c_t1 = ((t7 * t3.conj()).m(b) * t1).m(b)
-        return (((t2_t5_pow_q2 * t4_t1_pow_q3).m(b) * t6_t1c_pow_q1).m(b) * t7_t3c_t1).m(b)
+        t2_t5_pow_q2 = self.frob12_map(self.mul12(t2, t5), 2)
+        t4_t1_pow_q3 = self.frob12_map(self.mul12(t4, t1), 3)
+        t6_t1c_pow_q1 = self.frob12_map(self.mul12(t6, t1.conj()), 1)
+        t7_t3c_t1 = self.mul12(self.mul12(t7, t3.conj()), t1)
+        return self.mul12(self.mul12(self.mul12(t2_t5_pow_q2, t4_t1_pow_q3), t6_t1c_pow_q1), t7_t3c_t1)
 
     # ---- Miller loop with fused line evaluation (math.ts:1331-1388) --------------------------------
     def miller_loop(self, Px: Lin, Py: Lin, Qx: E2, Qy: E2, scaled=False) -> E12:
