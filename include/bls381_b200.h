@@ -197,7 +197,9 @@ int bls381_vm_load(const char* name, const uint8_t* image, size_t len);
  * Miller-product entry points give every lane that many consecutive items, which share the Fp12 squarings),
  * "swu_kernel" / "tail_kernels" / "g1_kernel" (default 1: hash_to_field + SWU, the tail of hash-to-curve and the sign
  * ladder, and G1 key decompression run as hand-written per-item kernels; 0 = the tower-VM programs of the same functions,
- * kept as the A/B path).  Results never depend on them.                                                          */
+ * kept as the A/B path), "pipeline_copies" (default 1: bls381_pairing_batch without a status array cuts batches of at
+ * least five rounds of resident CTAs into three chunks on two streams, so that only the first chunk's copy in and the last
+ * chunk's copy out are exposed; 0 = one copy in, one launch, one copy out).  Results never depend on them.           */
 int bls381_set_option(const char* name, int value);
 
 /* Measurement aids (bench.py): number of kernel launches (tower-VM and per-item kernels) since init, and a dependent-free

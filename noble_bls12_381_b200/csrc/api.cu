@@ -60,6 +60,7 @@ struct State {
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
     int swu_kernel = 1;  // hash-to-curve front (hash_to_field + SWU) as the hand-written kernel; 0 = all inside the tower-VM program (A/B)
     int g1_kernel = 1;   // G1 key decompression + subgroup check as a hand-written kernel; 0 = tower-VM program g1_decompress (A/B)
+    int pipeline_copies = 1;  // pairing_batch from host buffers: chunked H2D / kernel / D2H on two streams (0 = one copy in, one launch, one copy out)
     int tail_kernels = 1;  // tail of hash-to-curve / sign ladder as hand-written kernels (needs swu_kernel); 0 = tower-VM programs h2g2_tail / sign_tail (A/B)
     // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
     // verifyBatch at 131072 signatures on a B200: 1.26 / 1.39 / 1.42 / 1.40 M sigs/s for 1 / 2 / 3 / 4
@@ -753,6 +754,7 @@ int bls381_set_option(const char* name, int value) {
     else if (n == "swu_kernel") g.swu_kernel = value != 0;
     else if (n == "tail_kernels") g.tail_kernels = value != 0;
     else if (n == "g1_kernel") g.g1_kernel = value != 0;
+    else if (n == "pipeline_copies") g.pipeline_copies = value != 0;
     else if (n == "pairs_per_lane") g.pairs_per_lane = value;
     else return fail(BLS381_EINVAL, "unknown option: " + n);
     return BLS381_OK;
@@ -821,6 +823,38 @@ int bls381_pairing_batch(const uint8_t* g1, const uint8_t* g2, size_t n, int wit
     int rc;
     if ((rc = stage(0, n * 96)) || (rc = stage(1, n * 192)) || (rc = stage(2, n * 576))) return rc;
     if (status && (rc = stage(6, 3 * n * 4))) return rc;
+    // Large batches without validity checks: three chunks on the two internal streams, so that only the first chunk's
+    // H2D copy and the last chunk's D2H copy are exposed.  The kernels of consecutive chunks overlap: the persistent CTAs
+    // of the next chunk become resident as those of the previous one run out of batches, so there is still ONE tail.
+    const size_t round_items = (size_t)g.sm_count * 2 * 32;   // one batch per resident CTA of the 8-warp programs
+    if (!status && g.pipeline_copies && n >= 5 * round_items) {
+        const char* prog = with_final_exp ? "pairing" : "miller";
+        const size_t c0 = round_items, c2 = round_items, c1 = n - c0 - c2;
+        const size_t off[3] = {0, c0, c0 + c1}, len[3] = {c0, c1, c2};
+        cudaStream_t st[3] = {g.stream, g.stream2, g.stream};
+        CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));             // stream2 starts after everything queued so far
+        CUDA_TRY(cudaStreamWaitEvent(g.stream2, g.ev_fork, 0));
+        for (int c = 0; c < 3; ++c) {
+            CUDA_TRY(cudaMemcpyAsync(g.d_stage[0] + off[c] * 96, g1 + off[c] * 96, len[c] * 96, cudaMemcpyHostToDevice, st[c]));
+            CUDA_TRY(cudaMemcpyAsync(g.d_stage[1] + off[c] * 192, g2 + off[c] * 192, len[c] * 192, cudaMemcpyHostToDevice, st[c]));
+            if (c == 0) CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+            uint8_t* cb[3] = {g.d_stage[0] + off[c] * 96, g.d_stage[1] + off[c] * 192, g.d_stage[2] + off[c] * 576};
+            uint32_t cs[3] = {96, 192, 576};
+            if ((rc = vm_run(prog, cb, cs, 3, len[c], st[c]))) return rc;
+            if (c == 1) CUDA_TRY(cudaEventRecord(g.ev_join, g.stream2));
+            if (c == 2) {
+                CUDA_TRY(cudaStreamWaitEvent(g.stream, g.ev_join, 0));   // kernel time = first kernel start .. all kernels done
+                CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+            }
+            CUDA_TRY(cudaMemcpyAsync(out + off[c] * 576, g.d_stage[2] + off[c] * 576, len[c] * 576, cudaMemcpyDeviceToHost, st[c]));
+        }
+        CUDA_TRY(cudaStreamSynchronize(g.stream2));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+        g.last_ms = ms;
+        return BLS381_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], g1, n * 96, cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], g2, n * 192, cudaMemcpyHostToDevice, g.stream));
     uint8_t* bufs[3] = {g.d_stage[0], g.d_stage[1], g.d_stage[2]};
@@ -1375,6 +1409,9 @@ int bls381_sign_batch(const uint8_t* sks32, const uint8_t* msgs, const uint64_t*
     cudaStream_t s = g.stream;
     std::vector<uint8_t> dp;
     make_dst_prime(dst, dst_len, dp);
+    // (A chunked copy / compute pipeline like the one of bls381_pairing_batch was measured here and is NOT used: cutting the
+    // per-item kernels into chunks of two waves costs 5 % in drained waves, and kernels of different kinds sharing an SM on
+    // two streams cost 7 %; the copies are 2 % of the call.  profiles/r2_notes.md)
     if (mbytes) CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], msgs, mbytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[1], msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[7], sks32, n * 32, cudaMemcpyHostToDevice, s));

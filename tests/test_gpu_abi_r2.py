@@ -210,6 +210,26 @@ def test_random_pairs_config2_sample_vs_c_oracle(eng):
     assert raw == C.pairing_batch(g1[: 96 * 512], g2[: 192 * 512], 512, False)
 
 
+def test_chunked_copy_pipeline_of_pairing_batch_is_result_neutral(eng):
+    """bls381_pairing_batch from host buffers: the three-chunk, two-stream copy / compute pipeline (batches of at least five
+    rounds of resident CTAs, no status array) returns the bytes of the single-launch path, for the exponentiated pairing
+    and for the raw Miller loop, at a size that is not a multiple of the chunk or batch size."""
+    from noble_bls12_381_b200 import synth
+    from oracle import c_oracle as C
+    n = 5 * eng.sm_count() * 64 + 77
+    g1, g2 = synth.random_pairs_wire(eng, n, seed=0xC0FFEE)
+    try:
+        outs = {}
+        for mode in (1, 0):
+            eng.set_option("pipeline_copies", mode)
+            outs[mode] = (eng.pairing_batch(g1, g2, n, True), eng.pairing_batch(g1, g2, n, False))
+    finally:
+        eng.set_option("pipeline_copies", 1)
+    assert outs[0] == outs[1]
+    for k in (0, eng.sm_count() * 64 - 1, eng.sm_count() * 64, n - eng.sm_count() * 64 - 1, n - 1):   # around the chunk borders
+        assert outs[1][0][576 * k: 576 * k + 576] == C.pairing_batch(g1[96 * k: 96 * k + 96], g2[192 * k: 192 * k + 192], 1, True)
+
+
 # ---- wire formats end to end on the device against ALL 4 x 1000 zkcrypto vectors (test/deterministic.test.ts:49-113) -----
 def _zk(name):
     return open(os.path.join(GOLDEN, name), "rb").read()
