@@ -60,6 +60,7 @@ struct State {
     int no_tma = 0;      // disable TMA staging of the inputs (env BLS381_B200_NO_TMA, A/B testing)
     int swu_kernel = 1;  // hash-to-curve front (hash_to_field + SWU) as the hand-written kernel; 0 = all inside the tower-VM program (A/B)
     int g1_kernel = 1;   // G1 key decompression + subgroup check as a hand-written kernel; 0 = tower-VM program g1_decompress (A/B)
+    int g2_kernel = 1;  // batches of compressed signatures (fromSignature + assertValidity) as the hand-written per-item kernel; 0 = tower-VM program g2_decompress (A/B)
     int pipeline_copies = 1;  // pairing_batch from host buffers: chunked H2D / kernel / D2H on two streams (0 = one copy in, one launch, one copy out)
     int tail_kernels = 1;  // tail of hash-to-curve / sign ladder as hand-written kernels (needs swu_kernel); 0 = tower-VM programs h2g2_tail / sign_tail (A/B)
     // Miller-product lanes handle this many items (1..4) with shared Fp12 squarings (env BLS381_B200_PAIRS_PER_LANE);
@@ -468,6 +469,17 @@ int g1_decompress_dev(uint8_t* d_in, uint8_t* d_out, int32_t* d_status, size_t n
     return BLS381_OK;
 }
 
+// PointG2.fromSignature (96-byte signatures) + assertValidity: n x 96 B -> n x 192 B affine + status   (index.ts:500-530, 633-638)
+// Small batches keep the tower-VM program: its four warps work on one item set, a thread of the kernel runs the item alone
+// (1.8 ms against ~5 ms for a single signature).
+int g2_decompress_dev(uint8_t* d_in, uint8_t* d_out, int32_t* d_status, size_t n, cudaStream_t s) {
+    if (!g.g2_kernel || n < 256) return run3("g2_decompress", d_in, 96, d_out, 192, d_status, n, s);
+    swu::g2_decompress_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_out, d_status, n);
+    CUDA_TRY(cudaGetLastError());
+    g.launches.fetch_add(1);
+    return BLS381_OK;
+}
+
 // g.d_stage[4] (n x 256 uniform bytes) -> g.d_stage[10] (n x 576 B: the two points of E' per message), csrc/swu_g2.cuh
 int swu_points(size_t n, cudaStream_t s) {
     int rc;
@@ -605,6 +617,7 @@ int init_context(int device, const char* program_dir) {   // caller holds g.mu; 
     if (const char* e = getenv("BLS381_B200_NO_TMA")) g.no_tma = atoi(e);
     if (const char* e = getenv("BLS381_B200_SWU_KERNEL")) g.swu_kernel = atoi(e);
     if (const char* e = getenv("BLS381_B200_TAIL_KERNELS")) g.tail_kernels = atoi(e);
+    if (const char* e = getenv("BLS381_B200_G2_KERNEL")) g.g2_kernel = atoi(e);
     if (const char* e = getenv("BLS381_B200_G1_KERNEL")) g.g1_kernel = atoi(e);
     if (const char* e = getenv("BLS381_B200_PAIRS_PER_LANE")) g.pairs_per_lane = atoi(e);
     if (const char* e = getenv("BLS381_B200_DYNAMIC")) g.dynamic_batches = atoi(e);  // 0 = static round-robin batches
@@ -754,6 +767,7 @@ int bls381_set_option(const char* name, int value) {
     else if (n == "swu_kernel") g.swu_kernel = value != 0;
     else if (n == "tail_kernels") g.tail_kernels = value != 0;
     else if (n == "g1_kernel") g.g1_kernel = value != 0;
+    else if (n == "g2_kernel") g.g2_kernel = value != 0;
     else if (n == "pipeline_copies") g.pipeline_copies = value != 0;
     else if (n == "pairs_per_lane") g.pairs_per_lane = value;
     else return fail(BLS381_EINVAL, "unknown option: " + n);
@@ -964,7 +978,7 @@ int bls381_g2_decompress_batch(const uint8_t* in96, size_t n, uint8_t* out192, i
     int rc;
     if ((rc = stage(0, n * 96)) || (rc = stage(2, n * 192)) || (rc = stage(6, n * 4))) return rc;
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in96, n * 96, cudaMemcpyHostToDevice, g.stream));
-    if ((rc = run3("g2_decompress", g.d_stage[0], 96, g.d_stage[2], 192, (int32_t*)g.d_stage[6], n, g.stream))) return rc;
+    if ((rc = g2_decompress_dev(g.d_stage[0], g.d_stage[2], (int32_t*)g.d_stage[6], n, g.stream))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out192, g.d_stage[2], n * 192, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaMemcpyAsync(status, g.d_stage[6], n * 4, cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -1493,7 +1507,7 @@ static int aggregate_host(bool g2, const uint8_t* in, size_t n, uint8_t* out, in
     cudaStream_t s = g.stream;
     CUDA_TRY(cudaMemcpyAsync(g.d_stage[0], in, n * cb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(g.ev0, s));
-    if ((rc = g2 ? run3("g2_decompress", g.d_stage[0], cb, g.d_stage[8], 2 * cb, (int32_t*)g.d_stage[6], n, s)
+    if ((rc = g2 ? g2_decompress_dev(g.d_stage[0], g.d_stage[8], (int32_t*)g.d_stage[6], n, s)
                  : g1_decompress_dev(g.d_stage[0], g.d_stage[8], (int32_t*)g.d_stage[6], n, s)))
         return rc;
     if ((rc = aggregate_dev(g2, g.d_stage[8], (int32_t*)g.d_stage[6], n, g.d_stage[9], s))) return rc;

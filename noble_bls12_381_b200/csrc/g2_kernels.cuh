@@ -519,6 +519,99 @@ SWU_FN void g1_decompress_one(const uint8_t* in48, uint8_t* out96, int32_t* stat
     *status = flag_inf ? 1 : (no_sqrt ? 4 : (not_sub ? 3 : 0));   // BLS381_ST_INFINITY / BAD_ENCODING / NOT_IN_SUBGROUP / OK
 }
 
+// ---- G2: PointG2.fromSignature for 96-byte compressed signatures incl. assertValidity (index.ts:500-530, 633-638, 688-690)
+// Same decisions as the tower-VM program g2_decompress (vmprog/curves.py: build_g2_decompress): x = (z2 mod p) + (z1 mod 2^381
+// mod p) i, y = sqrt(x^3 + 4(1 + i)) with the sign rule of index.ts:522-526, subgroup test [-z]... psi(P) == [x]P.
+
+// sqrt in Fp2 by the complex method (two Fp exponentiations a^((p-3)/4) instead of the reference's 758-bit Fp2 power,
+// math.ts:486-507): n = a0^2 + a1^2, delta = sqrt(n), gamma = (a0 + delta)/2, root = s + a1/(2 s) i with s = sqrt(gamma), or,
+// when gamma is a non-residue, -a1/(2 s') + s' i with s'^2 = -gamma (same exponentiation).  ok = (root^2 == a), i.e. a is a
+// square: which of the two roots comes out does not matter, the caller fixes the sign.
+SWU_FN bool fe2_sqrt(Fe2& root, const Fe2& a) {
+    Fe n, e, delta, inv2, gamma, a1h, tpow, s, w, ss;
+    fe_dot2(n, a.c0.v, a.c0.v, a.c1.v, a.c1.v);
+    fe_pow_p34(e, n);
+    fe_mul(delta, n, e);
+    fe_set(inv2, kInv2);
+    fe_add(gamma, a.c0, delta);
+    fe_mul(gamma, gamma, inv2);
+    {   // gamma = 0 (a1 = 0 and a0 = -delta): take the other one, (a0 - delta)/2 = a0
+        const bool gz = fe_is_zero(gamma);
+        fe_sel(gamma, gz, a.c0, gamma);
+    }
+    fe_mul(a1h, a.c1, inv2);
+    fe_pow_p34(tpow, gamma);
+    fe_mul(s, gamma, tpow);
+    fe_mul(w, a1h, tpow);
+    fe_mul(ss, s, s);
+    const bool is_qr = fe_eq(ss, gamma);
+    Fe nw;
+    fe_neg(nw, w);
+    fe_sel(root.c0, is_qr, s, nw);
+    fe_sel(root.c1, is_qr, w, s);
+    Fe2 chk;
+    fe2_sqr(chk, root);
+    return fe_eq(chk.c0, a.c0) && fe_eq(chk.c1, a.c1);
+}
+
+// index.ts:688-690: psi(P) == [x]P = -[z]P, projective comparison
+SWU_FN bool g2_is_torsion_free(const G2p& p) {
+    G2p xP, ps;
+    g2_mul_x(xP, p);
+    fe2_neg(xP.Y, xP.Y);
+    g2_psi(ps, p);
+    Fe2 l, r;
+    fe2_mul(l, xP.X, ps.Z); fe2_mul(r, ps.X, xP.Z);
+    const bool xe = fe_eq(l.c0, r.c0) && fe_eq(l.c1, r.c1);
+    fe2_mul(l, xP.Y, ps.Z); fe2_mul(r, ps.Y, xP.Z);
+    return xe && fe_eq(l.c0, r.c0) && fe_eq(l.c1, r.c1);
+}
+
+// one signature: 96 B compressed (x.c1 || x.c0 with the flag bits) -> 192 B affine (x.c0, x.c1, y.c0, y.c1; plain big-endian) + status
+SWU_FN void g2_decompress_one(const uint8_t* in96, uint8_t* out192, int32_t* status) {
+    const bool flag_inf = (in96[0] >> 6) & 1, aflag = (in96[0] >> 5) & 1;
+    Fe raw, c, t;
+    Fe2 x, xx, y2, y;
+    fe_set(c, kR2);
+    fe_load_be(raw, in96);
+    raw.v[11] &= 0x1FFFFFFFu;                  // z1 mod 2^381 -> imaginary part (index.ts:510)
+    fe_mul(x.c1, raw, c);                      // reduced mod p like `new Fp`, Montgomery form
+    fe_load_be(raw, in96 + 48);                // z2 (any 384-bit value) -> real part
+    fe_mul(x.c0, raw, c);
+    fe2_sqr(xx, x);
+    fe2_mul(y2, xx, x);
+    fe_set(c, kFour);
+    fe_add(y2.c0, y2.c0, c);
+    fe_add(y2.c1, y2.c1, c);                   // x^3 + 4 (1 + i)
+    const bool found = fe2_sqrt(y, y2);
+    Fe p1, p0;
+    fe_plain(p1, y.c1);
+    const bool y1_zero = fe_is_zero(p1), g1 = fe_gt_half(p1);
+    fe_plain(p0, y.c0);
+    const bool g0 = fe_gt_half(p0);
+    // isGreater = y1 > 0 && (y1*2)/P != aflag ; isZero = y1 == 0 && (y0*2)/P != aflag      (index.ts:522-526)
+    const bool flip = y1_zero ? (g0 != aflag) : (g1 != aflag);
+    Fe2 ny;
+    fe2_neg(ny, y);
+    fe2_sel(y, flip, ny, y);
+    G2p pt;
+    pt.X = x; pt.Y = y; fe_set(pt.Z.c0, kOne); fe_zero(pt.Z.c1);
+    const bool not_sub = !g2_is_torsion_free(pt);
+    fe_plain(t, x.c0); fe_store_be(out192, t);
+    fe_plain(t, x.c1); fe_store_be(out192 + 48, t);
+    fe_plain(t, y.c0); fe_store_be(out192 + 96, t);
+    fe_plain(t, y.c1); fe_store_be(out192 + 144, t);
+    *status = flag_inf ? 1 : (!found ? 5 : (not_sub ? 3 : 0));   // BLS381_ST_INFINITY / NO_SQRT / NOT_IN_SUBGROUP / OK
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(128, 4) g2_decompress_kernel(const uint8_t* in96, uint8_t* out192, int32_t* status, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_decompress_one(in96 + 96 * i, out192 + 192 * i, status + i);
+}
+#endif
+
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(128, 4) g1_decompress_kernel(const uint8_t* in48, uint8_t* out96, int32_t* status, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

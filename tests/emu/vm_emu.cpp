@@ -40,6 +40,9 @@ void emu_sign_tail(const uint8_t* in, const uint8_t* digits, uint8_t* out, size_
 void emu_g1_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
     for (size_t i = 0; i < n; ++i) swu::g1_decompress_one(in + 48 * i, out + 96 * i, st + i);
 }
+void emu_g2_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
+    for (size_t i = 0; i < n; ++i) swu::g2_decompress_one(in + 96 * i, out + 192 * i, st + i);
+}
 // products / reductions executed by the swu / g2 kernels' source since the last call (host-build counters)
 void emu_swu_counters(long* out2) { out2[0] = swu::g_products; out2[1] = swu::g_reductions; swu::g_products = swu::g_reductions = 0; }
 

@@ -363,3 +363,31 @@ def test_per_item_kernels_equal_the_tower_vm_programs(eng):
     for x, y in ((a, b), (a, c)):
         assert x[0] == y[0] and x[1] == y[1] and x[3] == y[3] and x[4] == y[4] and x[5] == y[5]
         assert all(x[2][96 * i: 96 * i + 96] == y[2][96 * i: 96 * i + 96] for i in range(n) if x[3][i] == 0)
+
+
+def test_g2_decompress_kernel_equals_program_and_oracle(eng):
+    """PointG2.fromSignature + assertValidity for batches (csrc/g2_kernels.cuh g2_decompress_kernel) against the tower-VM
+    program of the same function and the oracle's expectations: zkcrypto vectors, random signatures, no square root, outside
+    the subgroup, infinity flag with junk, non-canonical encodings; aggregateSignatures over the batch path."""
+    from tests.test_vm_ingest_emu import _g2_cases, g2_expected
+    g2c = open(os.path.join(GOLDEN, "zkcrypto_g2_compressed.dat"), "rb").read()
+    items = _g2_cases() + [g2c[96 * i: 96 * i + 96] for i in range(1, 1000)]
+    n = len(items)
+    assert n >= 256   # the kernel path (smaller batches keep the program)
+    try:
+        eng.set_option("g2_kernel", 1)
+        k_out, k_st = eng.g2_decompress_batch(b"".join(items), n)
+        agg_k = eng.aggregate_g2(b"".join(items[-999:]), 999)
+        eng.set_option("g2_kernel", 0)
+        p_out, p_st = eng.g2_decompress_batch(b"".join(items), n)
+        agg_p = eng.aggregate_g2(b"".join(items[-999:]), 999)
+    finally:
+        eng.set_option("g2_kernel", 1)
+    assert list(k_st) == list(p_st)
+    assert agg_k[0] == agg_p[0] and list(agg_k[1]) == list(agg_p[1])
+    for i, it in enumerate(items[:40]):
+        exp_st, exp = g2_expected(it)
+        assert k_st[i] == exp_st, i
+        if exp is not None:
+            assert k_out[192 * i: 192 * i + 192] == exp, i
+    assert all(k_out[192 * i: 192 * i + 192] == p_out[192 * i: 192 * i + 192] for i in range(n) if k_st[i] in (0, 3))

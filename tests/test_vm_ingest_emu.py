@@ -174,6 +174,23 @@ def test_g2_decompress_program():
             assert bytes(out[192 * i : 192 * i + 192]) == exp, i
 
 
+def test_g2_decompress_kernel_source():
+    """csrc/g2_kernels.cuh g2_decompress_one (host build of the kernel's source: complex-method square root, sign rule,
+    psi subgroup test) on the same cases as the tower-VM program."""
+    import ctypes
+    items = _g2_cases()
+    n = len(items)
+    out = (ctypes.c_uint8 * (192 * n))()
+    st = (ctypes.c_int32 * n)()
+    emu.lib().emu_g2_decompress(b"".join(items), out, st, ctypes.c_size_t(n))
+    out = bytes(out)
+    for i, it in enumerate(items):
+        exp_st, exp = g2_expected(it)
+        assert st[i] == exp_st, i
+        if exp is not None:
+            assert out[192 * i : 192 * i + 192] == exp, i
+
+
 def test_hash_to_g2_program():
     b = vmcompile.compile_program("hash_to_g2")
     msgs = [b"", b"abc", bytes(range(32)), b"x" * 100, bytes.fromhex("d2")]
