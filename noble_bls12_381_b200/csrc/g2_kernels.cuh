@@ -612,6 +612,79 @@ __global__ void __launch_bounds__(128, 4) g2_decompress_kernel(const uint8_t* in
 }
 #endif
 
+// ---- getPublicKey (index.ts:738-740): sk * G1 with a fixed-base table -------------------------------------------------
+// table[w][d - 1] = (d * 16^w) G1, affine, Montgomery form (tools/gen_g1_comb.py): sk * G1 = sum over the 64 nibbles of sk of
+// one table point -- 64 complete mixed additions and no doubling.  Constant time in the key: every entry of a window is
+// read and selected arithmetically, a zero nibble is a select on the sum; all threads read the same addresses (broadcast).
+struct G1a { Fe x, y; };
+
+// complete mixed addition (RCB15 algorithm 8, a = 0): g1_add with q = (x, y, 1); p may be infinity, q is not
+SWU_FN void g1_madd(G1p& r, const G1p& p, const G1a& q) {
+    Fe A, B, D, E, F, bC, bF, A3, t0, t2, X3, Y3, Z3;
+    uint32_t nE[12];
+    fe_mul(A, p.X, q.x);
+    fe_mul(B, p.Y, q.y);
+    fe_dot2(D, p.X.v, q.y.v, q.x.v, p.Y.v);
+    fe_mul(E, q.y, p.Z); fe_add(E, E, p.Y);
+    fe_mul(F, q.x, p.Z); fe_add(F, F, p.X);
+    fe_mul12(bC, p.Z);
+    fe_mul12(bF, F);
+    fe_add(A3, A, A); fe_add(A3, A3, A);
+    fe_sub(t2, B, bC);
+    fe_add(t0, B, bC);
+    fpc::neg_raw(nE, E.v);
+    fe_dot2(X3, D.v, t2.v, nE, bF.v);
+    fe_dot2(Y3, t0.v, t2.v, A3.v, bF.v);
+    fe_dot2(Z3, E.v, t0.v, A3.v, D.v);
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
+// one key: 32-byte big-endian scalar (already reduced mod r) -> 96 B affine (x || y, plain big-endian) + flag word (2 = infinity)
+SWU_FN void g1_fixed_base_one(const uint8_t* sk32, const uint32_t* table, uint8_t* out96, int32_t* flag) {
+    G1p acc, sum;
+    fe_zero(acc.X); fe_set(acc.Y, kOne); fe_zero(acc.Z);
+#pragma unroll 1
+    for (int w = 0; w < 64; ++w) {
+        const uint32_t byte = sk32[31 - (w >> 1)];
+        const uint32_t idx = (w & 1) ? (byte >> 4) : (byte & 15u);
+        const uint32_t* tw = table + (size_t)w * 15 * 24;
+        G1a sel;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { sel.x.v[k] = tw[k]; sel.y.v[k] = tw[12 + k]; }
+#pragma unroll 1
+        for (uint32_t d = 2; d < 16; ++d) {
+            const uint32_t* e = tw + (d - 1) * 24;
+            const bool take = d == idx;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                sel.x.v[k] = take ? e[k] : sel.x.v[k];
+                sel.y.v[k] = take ? e[12 + k] : sel.y.v[k];
+            }
+        }
+        g1_madd(sum, acc, sel);
+        const bool add = idx != 0;
+        fe_sel(acc.X, add, sum.X, acc.X);
+        fe_sel(acc.Y, add, sum.Y, acc.Y);
+        fe_sel(acc.Z, add, sum.Z, acc.Z);
+    }
+    const bool is_inf = fe_is_zero(acc.Z);
+    Fe zi, x, y, t;
+    fpc::fp_inv_mont(zi.v, acc.Z.v);
+    fe_mul(x, acc.X, zi);
+    fe_mul(y, acc.Y, zi);
+    fe_plain(t, x); fe_store_be(out96, t);
+    fe_plain(t, y); fe_store_be(out96 + 48, t);
+    *flag = is_inf ? 2 : 0;
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(128, 4) g1_fixed_base_kernel(const uint8_t* sk32, const uint32_t* table, uint8_t* out96, int32_t* flags, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_fixed_base_one(sk32 + 32 * i, table, out96 + 96 * i, flags + i);
+}
+#endif
+
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(128, 4) g1_decompress_kernel(const uint8_t* in48, uint8_t* out96, int32_t* status, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

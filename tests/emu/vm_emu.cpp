@@ -9,6 +9,7 @@
 #include "../../noble_bls12_381_b200/csrc/vm.cuh"
 #include "../../noble_bls12_381_b200/csrc/fp_inv.cuh"
 #include "../../noble_bls12_381_b200/csrc/swu_g2.cuh"
+#include "../../noble_bls12_381_b200/csrc/g1_comb_gen.cuh"
 #include "../../noble_bls12_381_b200/csrc/g2_kernels.cuh"
 
 extern "C" {
@@ -39,6 +40,9 @@ void emu_sign_tail(const uint8_t* in, const uint8_t* digits, uint8_t* out, size_
 
 void emu_g1_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
     for (size_t i = 0; i < n; ++i) swu::g1_decompress_one(in + 48 * i, out + 96 * i, st + i);
+}
+void emu_g1_fixed_base(const uint8_t* sk32, uint8_t* out, int32_t* flags, size_t n) {
+    for (size_t i = 0; i < n; ++i) swu::g1_fixed_base_one(sk32 + 32 * i, swu::kG1Comb, out + 96 * i, flags + i);
 }
 void emu_g2_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
     for (size_t i = 0; i < n; ++i) swu::g2_decompress_one(in + 96 * i, out + 192 * i, st + i);

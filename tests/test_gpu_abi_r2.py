@@ -391,3 +391,23 @@ def test_g2_decompress_kernel_equals_program_and_oracle(eng):
         if exp is not None:
             assert k_out[192 * i: 192 * i + 192] == exp, i
     assert all(k_out[192 * i: 192 * i + 192] == p_out[192 * i: 192 * i + 192] for i in range(n) if k_st[i] in (0, 3))
+
+
+def test_fixed_base_get_public_key_equals_the_ladder_program(eng):
+    """getPublicKey: the fixed-base table kernel (64 mixed additions, csrc/g2_kernels.cuh g1_fixed_base_kernel) and the
+    constant-time ladder program g1_scalar_mul give the same 48 bytes on edge and random keys (incl. unreduced ones), and
+    both match the C oracle."""
+    from oracle import c_oracle as C
+    rng = random.Random(5)
+    ks = [1, 2, 15, 16, 17, 1 << 252, R_ORDER - 1, R_ORDER + 5, (1 << 256) - 1, int("f" * 62, 16)] + [rng.getrandbits(256) for _ in range(500)]
+    sks = b"".join(k.to_bytes(32, "big") for k in ks)
+    try:
+        eng.set_option("fixed_base", 1)
+        a = eng.get_public_key_batch(sks)
+        eng.set_option("fixed_base", 0)
+        b = eng.get_public_key_batch(sks)
+    finally:
+        eng.set_option("fixed_base", 1)
+    assert a == b
+    red = b"".join((k % R_ORDER).to_bytes(32, "big") for k in ks[:64])
+    assert a[: 48 * 64] == C.get_public_key_batch(red)

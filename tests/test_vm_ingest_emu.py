@@ -174,6 +174,26 @@ def test_g2_decompress_program():
             assert bytes(out[192 * i : 192 * i + 192]) == exp, i
 
 
+def test_g1_fixed_base_kernel_source():
+    """getPublicKey through the fixed-base table (csrc/g2_kernels.cuh g1_fixed_base_one, table from tools/gen_g1_comb.py):
+    edge scalars (single nibbles, zero nibbles, all-ones nibbles, r - 1, 0) and random ones against the oracle."""
+    import ctypes
+    rng = random.Random(11)
+    ks = [1, 2, 15, 16, 17, 0xF0, 1 << 252, (1 << 252) + 1, O.R_ORDER - 1, 0, 0x0F0F0F0F0F0F0F0F, int("f" * 62, 16)]
+    ks += [rng.randrange(1, O.R_ORDER) for _ in range(12)]
+    n = len(ks)
+    out = (ctypes.c_uint8 * (96 * n))()
+    fl = (ctypes.c_int32 * n)()
+    emu.lib().emu_g1_fixed_base(b"".join(k.to_bytes(32, "big") for k in ks), out, fl, ctypes.c_size_t(n))
+    out = bytes(out)
+    for i, k in enumerate(ks):
+        if k % O.R_ORDER == 0:
+            assert fl[i] == 2, i
+            continue
+        x, y = O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, k))[:2]
+        assert fl[i] == 0 and out[96 * i : 96 * i + 96] == x.to_bytes(48, "big") + y.to_bytes(48, "big"), i
+
+
 def test_g2_decompress_kernel_source():
     """csrc/g2_kernels.cuh g2_decompress_one (host build of the kernel's source: complex-method square root, sign rule,
     psi subgroup test) on the same cases as the tower-VM program."""
