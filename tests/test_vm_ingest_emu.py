@@ -174,6 +174,25 @@ def test_g2_decompress_program():
             assert bytes(out[192 * i : 192 * i + 192]) == exp, i
 
 
+def test_fixed_base_table_is_reproducible_and_correct(tmp_path):
+    """csrc/g1_comb_gen.cuh is what tools/gen_g1_comb.py writes, and its entries are (d * 16^w) G1 by the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "noble_bls12_381_b200", "csrc", "g1_comb_gen.cuh")
+    out = tmp_path / "comb.cuh"
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_g1_comb.py"), str(out)])
+    assert out.read_text() == open(hdr).read()
+    rows = [l for l in open(hdr) if l.startswith("    0x")]
+    assert len(rows) == 64 * 15
+    rinv = pow(1 << 384, -1, O.P)
+    for w, d in ((0, 1), (0, 15), (1, 1), (31, 9), (63, 15)):
+        words = [int(t.strip().rstrip("u"), 16) for t in rows[w * 15 + d - 1].split("//")[0].split(",") if t.strip()]
+        x = sum(v << (32 * i) for i, v in enumerate(words[:12])) * rinv % O.P
+        y = sum(v << (32 * i) for i, v in enumerate(words[12:24])) * rinv % O.P
+        assert (x, y) == tuple(O.pt_to_affine(O.G1, O.pt_multiply_unsafe(O.G1, O.G1_BASE, d * 16**w % O.R_ORDER))[:2])
+
+
 def test_g1_fixed_base_kernel_source():
     """getPublicKey through the fixed-base table (csrc/g2_kernels.cuh g1_fixed_base_one, table from tools/gen_g1_comb.py):
     edge scalars (single nibbles, zero nibbles, all-ones nibbles, r - 1, 0) and random ones against the oracle."""
