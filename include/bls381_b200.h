@@ -195,8 +195,9 @@ int bls381_vm_load(const char* name, const uint8_t* image, size_t len);
  * claim 32-item batches from a global counter, 0 = round-robin), "ctas_per_sm" (0 = automatic), "poll_sleep_ns",
  * "no_tma" (1 = read wire-format inputs directly from global memory), "pairs_per_lane" (1..4, default 3: the
  * Miller-product entry points give every lane that many consecutive items, which share the Fp12 squarings),
- * "swu_kernel" / "tail_kernels" / "g1_kernel" / "g2_kernel" (default 1: hash_to_field + SWU, the tail of hash-to-curve and
- * the sign ladder, G1 key decompression and batches of compressed signatures run as hand-written per-item kernels; 0 = the tower-VM programs of the same functions,
+ * "swu_kernel" / "tail_kernels" / "g1_kernel" / "g2_kernel" / "validate_kernels" (default 1: hash_to_field + SWU, the tail of hash-to-curve and
+ * the sign ladder, G1 key decompression, batches of compressed signatures and the validity checks of affine points run as hand-written
+ * per-item kernels; 0 = the tower-VM programs of the same functions,
  * kept as the A/B path), "fixed_base" (default 1: getPublicKey adds 64 points of a fixed-base table of G1, one per nibble of
  * the key, every table entry read for every key; 0 = the constant-time ladder program g1_scalar_mul), "pipeline_copies" (default 1: bls381_pairing_batch without a status array cuts batches of at
  * least five rounds of resident CTAs into three chunks on two streams, so that only the first chunk's copy in and the last

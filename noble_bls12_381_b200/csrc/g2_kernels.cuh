@@ -685,6 +685,60 @@ __global__ void __launch_bounds__(128, 4) g1_fixed_base_kernel(const uint8_t* sk
 }
 #endif
 
+// ---- assertValidity of affine points (index.ts:383-388, 633-638): on the curve, then in the prime-order subgroup ----------
+// Same status words as the tower-VM programs g1_validate / g2_validate; coordinates are 48-byte big-endian values reduced
+// mod p like `new Fp`.  Used by pairing() with a status array (index.ts:717-718).
+SWU_FN void fe_from_be48(Fe& r, const uint8_t* p) {
+    Fe raw, c;
+    fe_load_be(raw, p);
+    fe_set(c, kR2);
+    fe_mul(r, raw, c);
+}
+SWU_FN void g1_validate_one(const uint8_t* in96, int32_t* status) {
+    G1p pt;
+    Fe t, l, c;
+    fe_from_be48(pt.X, in96);
+    fe_from_be48(pt.Y, in96 + 48);
+    fe_set(pt.Z, kOne);
+    fe_mul(t, pt.X, pt.X);
+    fe_mul(t, t, pt.X);
+    fe_set(c, kFour);
+    fe_add(t, t, c);                                   // x^3 + 4
+    fe_mul(l, pt.Y, pt.Y);
+    const bool on = fe_eq(l, t);
+    const bool sub = g1_is_torsion_free(pt);
+    *status = !on ? 2 : (!sub ? 3 : 0);                // BLS381_ST_NOT_ON_CURVE / NOT_IN_SUBGROUP / OK
+}
+SWU_FN void g2_validate_one(const uint8_t* in192, int32_t* status) {
+    G2p pt;
+    Fe2 t, l;
+    Fe c;
+    fe_from_be48(pt.X.c0, in192); fe_from_be48(pt.X.c1, in192 + 48);
+    fe_from_be48(pt.Y.c0, in192 + 96); fe_from_be48(pt.Y.c1, in192 + 144);
+    fe_set(pt.Z.c0, kOne); fe_zero(pt.Z.c1);
+    fe2_sqr(t, pt.X);
+    fe2_mul(t, t, pt.X);
+    fe_set(c, kFour);
+    fe_add(t.c0, t.c0, c); fe_add(t.c1, t.c1, c);      // x^3 + 4 (1 + i)
+    fe2_sqr(l, pt.Y);
+    const bool on = fe_eq(l.c0, t.c0) && fe_eq(l.c1, t.c1);
+    const bool sub = g2_is_torsion_free(pt);
+    *status = !on ? 2 : (!sub ? 3 : 0);
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(128, 4) g1_validate_kernel(const uint8_t* in96, int32_t* status, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_validate_one(in96 + 96 * i, status + i);
+}
+__global__ void __launch_bounds__(128, 4) g2_validate_kernel(const uint8_t* in192, int32_t* status, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_validate_one(in192 + 192 * i, status + i);
+}
+#endif
+
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(128, 4) g1_decompress_kernel(const uint8_t* in48, uint8_t* out96, int32_t* status, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

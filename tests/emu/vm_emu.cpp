@@ -44,6 +44,12 @@ void emu_g1_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
 void emu_g1_fixed_base(const uint8_t* sk32, uint8_t* out, int32_t* flags, size_t n) {
     for (size_t i = 0; i < n; ++i) swu::g1_fixed_base_one(sk32 + 32 * i, swu::kG1Comb, out + 96 * i, flags + i);
 }
+void emu_validate(int g2, const uint8_t* in, int32_t* st, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (g2) swu::g2_validate_one(in + 192 * i, st + i);
+        else swu::g1_validate_one(in + 96 * i, st + i);
+    }
+}
 void emu_g2_decompress(const uint8_t* in, uint8_t* out, int32_t* st, size_t n) {
     for (size_t i = 0; i < n; ++i) swu::g2_decompress_one(in + 96 * i, out + 192 * i, st + i);
 }

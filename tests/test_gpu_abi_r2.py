@@ -411,3 +411,42 @@ def test_fixed_base_get_public_key_equals_the_ladder_program(eng):
     assert a == b
     red = b"".join((k % R_ORDER).to_bytes(32, "big") for k in ks[:64])
     assert a[: 48 * 64] == C.get_public_key_batch(red)
+
+
+def test_validate_kernels_equal_the_programs(eng):
+    """assertValidity of batches of affine points (g1_validate_kernel / g2_validate_kernel) against the tower-VM programs:
+    valid points, corrupted coordinates (off the curve), on-curve points outside the subgroup."""
+    from noble_bls12_381_b200 import synth
+    from tests.test_vm_ingest_emu import O
+    n = 600
+    g1, g2 = synth.random_pairs_wire(eng, n, seed=0x5EED)
+    g1, g2 = bytearray(g1), bytearray(g2)
+    for i in range(0, n, 7):          # off the curve
+        g1[96 * i + 95] ^= 1
+        g2[192 * i + 191] ^= 1
+    x = 1                              # on the curve, outside the subgroup
+    while True:
+        x += 1
+        y = O.fp_sqrt((x**3 + 4) % O.P)
+        if y is not None and not O.g1_is_torsion_free((x, y, 1)):
+            break
+    g1[96 * 3: 96 * 4] = x.to_bytes(48, "big") + y.to_bytes(48, "big")
+    xx = (1, 1)
+    while True:
+        xx = (xx[0] + 1, xx[1])
+        yy = O.fp2_sqrt(O.fp2_add(O.fp2_pow(xx, 3), O.B2))
+        if yy is not None and not O.g2_is_torsion_free((xx, yy, O.FP2_ONE)):
+            break
+    g2[192 * 3: 192 * 4] = b"".join(v.to_bytes(48, "big") for v in (xx[0], xx[1], yy[0], yy[1]))
+    g1, g2 = bytes(g1), bytes(g2)
+    try:
+        res = {}
+        for mode in (1, 0):
+            eng.set_option("validate_kernels", mode)
+            res[mode] = (list(eng.g1_validate_batch(g1, n)), list(eng.g2_validate_batch(g2, n)), eng.pairing_batch_checked(g1, g2, n, True))
+    finally:
+        eng.set_option("validate_kernels", 1)
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    assert res[0][2][1] == res[1][2][1] and res[0][2][0] == res[1][2][0]
+    assert res[1][0][0] == 2 and res[1][0][3] == 3 and res[1][0][1] == 0
+    assert res[1][1][0] == 2 and res[1][1][3] == 3 and res[1][1][1] == 0

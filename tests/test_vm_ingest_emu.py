@@ -473,8 +473,15 @@ def test_validate_programs_edge_points():
     pts.append((5, 7)); exp.append(curves.ST_NOT_ON_CURVE)
     n = len(pts)
     st = bytearray(4 * n)
-    emu.run_program(b1, {0: (bytearray(b"".join(a.to_bytes(48, "big") + c.to_bytes(48, "big") for a, c in pts)), 96), 5: (st, 4)}, n)
+    raw1 = b"".join(a.to_bytes(48, "big") + c.to_bytes(48, "big") for a, c in pts)
+    emu.run_program(b1, {0: (bytearray(raw1), 96), 5: (st, 4)}, n)
     assert list(struct.unpack("<%di" % n, st)) == exp
+    # the per-item kernel's source (csrc/g2_kernels.cuh g1_validate_one), host build, same cases + a coordinate >= p
+    import ctypes
+    raw1 += (pts[0][0] + O.P).to_bytes(48, "big") + pts[0][1].to_bytes(48, "big")
+    kst = (ctypes.c_int32 * (n + 1))()
+    emu.lib().emu_validate(0, raw1, kst, ctypes.c_size_t(n + 1))
+    assert list(kst) == exp + [0]
     # ---- G2
     b2 = vmcompile.compile_program("g2_validate")
     pts, exp = [], []
@@ -501,6 +508,9 @@ def test_validate_programs_edge_points():
     raw = b"".join(b"".join(v.to_bytes(48, "big") for v in (a[0], a[1], c[0], c[1])) for a, c in pts)
     emu.run_program(b2, {0: (bytearray(raw), 192), 5: (st, 4)}, n)
     assert list(struct.unpack("<%di" % n, st)) == exp
+    kst = (ctypes.c_int32 * n)()
+    emu.lib().emu_validate(1, raw, kst, ctypes.c_size_t(n))   # g2_validate_one, host build
+    assert list(kst) == exp
 
 
 def test_from_uncompressed_programs():
