@@ -68,7 +68,7 @@ def issued_imad_per_item(program_path, wide_per_product=144):
 # csrc/g2_kernels.cuh), counted by the host build of the same source (tests/test_vm_ingest_emu.py pins these numbers to the
 # counters); a product = 144, a reduction = 156 IMAD.WIDE.  The Fp inversion of the affine conversion is not included
 # (the tower-VM image counts leave its inversion record out as well).
-KERNEL_COUNTS = {"swu_g2_kernel": (2030, 1964), "h2g2_tail_kernel": (3842, 2217), "sign_kernel": (9648, 4478),
+KERNEL_COUNTS = {"swu_g2_kernel": (2030, 1964), "h2g2_tail_kernel": (3842, 2217), "sign_kernel": (8382, 4738),
                  "g1_decompress_kernel": (1632, 1446)}
 
 

@@ -128,6 +128,30 @@ SWU_FN void g2_dbl_jacobian(G2p& r, const G2p& p) {
     r.X = X3; r.Y = Y3; r.Z = Z3;
 }
 
+// Jacobian mixed addition (madd-2007-bl): p = (X/Z^2, Y/Z^3) Jacobian, q affine; 7 products + 4 squarings.  NOT complete:
+// p must not be infinity, +-q (the sign ladder guarantees it, see sign_one).
+SWU_FN void g2_madd_jacobian(G2p& r, const G2p& p, const Fe2& qx, const Fe2& qy) {
+    Fe2 ZZ, U2, S2, H, HH, I, J, rr, V, t, X3, Y3, Z3;
+    fe2_sqr(ZZ, p.Z);
+    fe2_mul(U2, qx, ZZ);
+    fe2_mul(t, p.Z, ZZ); fe2_mul(S2, qy, t);
+    fe2_sub(H, U2, p.X);
+    fe2_sqr(HH, H);
+    fe2_dbl(I, HH); fe2_dbl(I, I);                      // 4 HH
+    fe2_mul(J, H, I);
+    fe2_sub(rr, S2, p.Y); fe2_dbl(rr, rr);              // 2 (S2 - Y1)
+    fe2_mul(V, p.X, I);
+    fe2_sqr(X3, rr); fe2_sub(X3, X3, J); fe2_dbl(t, V); fe2_sub(X3, X3, t);
+    fe2_sub(t, V, X3);
+    {
+        Fe2 yj;
+        fe2_dbl(yj, p.Y);
+        fe2_mul2(Y3, rr, t, yj, J, true);                // r (V - X3) - 2 Y1 J
+    }
+    fe2_add(t, p.Z, H); fe2_sqr(Z3, t); fe2_sub(Z3, Z3, ZZ); fe2_sub(Z3, Z3, HH);
+    r.X = X3; r.Y = Y3; r.Z = Z3;
+}
+
 SWU_INL void g2_neg(G2p& r, const G2p& p) { r.X = p.X; fe2_neg(r.Y, p.Y); r.Z = p.Z; }
 
 SWU_FN void g2_psi(G2p& r, const G2p& p) {  // math.ts:1398-1403 on projective coordinates
@@ -355,9 +379,17 @@ SWU_FN void sign_one(const uint8_t* in576, const uint8_t* digits32, uint8_t* out
         for (int b = 0; b < 8; ++b) v = (v << 8) | digits32[8 * (3 - d) + b];
         a[d] = v;
     }
+    // The accumulator is JACOBIAN: dbl-2009-l + madd-2007-bl are 20 + 36 products per step instead of the 28 + 48 of the
+    // complete formulas.  The incomplete addition is safe here: once the first non-zero digit pattern has been added the
+    // accumulator is [2 m] H(m) with 0 < m, and a table entry [t] H(m) equals +-[2 m] H(m) only if every digit bit of t is
+    // even, i.e. t = 0 (both multipliers are sums of b_i z^i below z^4 < r).  Until then the accumulator is infinity and
+    // the "sum" is the table entry itself -- a select on a flag, no branch.
     G2p acc, sum;
-    fe_zero(acc.X.c0); fe_zero(acc.X.c1); fe_set(acc.Y.c0, kOne); fe_zero(acc.Y.c1); fe_zero(acc.Z.c0); fe_zero(acc.Z.c1);
+    fe_set(acc.X.c0, kOne); fe_zero(acc.X.c1); fe_set(acc.Y.c0, kOne); fe_zero(acc.Y.c1); fe_zero(acc.Z.c0); fe_zero(acc.Z.c1);
+    bool started = false;   // the accumulator is not infinity
     G2a sel;
+    Fe2 one2;
+    fe_set(one2.c0, kOne); fe_zero(one2.c1);
 #pragma unroll 1
     for (int j = 63; j >= 0; --j) {
         const uint32_t idx = (uint32_t)((a[0] >> j) & 1ull) | ((uint32_t)((a[1] >> j) & 1ull) << 1) |
@@ -368,14 +400,27 @@ SWU_FN void sign_one(const uint8_t* in576, const uint8_t* digits32, uint8_t* out
             fe2_sel(sel.x, k == idx, tab[k].X, sel.x);
             fe2_sel(sel.y, k == idx, tab[k].Y, sel.y);
         }
-        if (j != 63) g2_dbl(acc, acc);
-        g2_madd(sum, acc, sel);
-        g2_cmov(acc, idx != 0, sum);
+        if (j != 63) g2_dbl_jacobian(acc, acc);           // infinity (Z = 0) stays infinity
+        g2_madd_jacobian(sum, acc, sel.x, sel.y);
+        // not started: the sum is the table entry itself (x, y, 1)
+        fe2_sel(sum.X, started, sum.X, sel.x);
+        fe2_sel(sum.Y, started, sum.Y, sel.y);
+        fe2_sel(sum.Z, started, sum.Z, one2);
+        const bool add = idx != 0;
+        g2_cmov(acc, add, sum);
+        started = started | add;
     }
     if (h_inf) { fe_zero(acc.Z.c0); fe_zero(acc.Z.c1); }
     const bool is_inf = fe2_is_zero(acc.Z);
     Fe2 x, y;
-    g2_to_affine(x, y, acc);
+    {   // Jacobian -> affine: x = X / Z^2, y = Y / Z^3
+        Fe2 zi, zi2, zi3;
+        fe2_inv(zi, acc.Z);
+        fe2_sqr(zi2, zi);
+        fe2_mul(zi3, zi2, zi);
+        fe2_mul(x, acc.X, zi2);
+        fe2_mul(y, acc.Y, zi3);
+    }
     // (one temporary on purpose: with four live results of fe_plain the sm_100a build returned the same value for all of
     // them -- found by the KAT tests, the host build was right; this form is the one h2g2_tail_one uses)
     Fe t;
