@@ -412,6 +412,30 @@ def test_tail_kernels_source_against_oracle_and_kats():
         assert sig[96 * i : 96 * i + 96].hex() == want, i
 
 
+def test_sign_ladder_digit_patterns_against_the_c_oracle():
+    """The Jacobian sign ladder of csrc/g2_kernels.cuh (host build): scalars whose base-|x| digits have long leading-zero runs,
+    zero digits, single bits and all-ones patterns -- the cases in which the accumulator stays at infinity, starts late, or
+    adds nothing for many steps -- plus random scalars, against the C oracle's sign()."""
+    import ctypes
+    from oracle import c_oracle as C
+    rng = random.Random(2024)
+    z = 0xD201000000010000
+    ks = [1 << 63, (1 << 63) + 1, z * ((1 << 63) | 1), z**2 * 3 + 1, z**3 * 5, z**3 + z, (1 << 32) - 1, 1 << 200,
+          (z - 1) * (1 + z + z * z), z**3 * (1 << 60) + (1 << 62), 0x5555555555555555, 0xAAAAAAAAAAAAAAAA * z]
+    ks = [k % O.R_ORDER for k in ks if k % O.R_ORDER] + [rng.randrange(1, O.R_ORDER) for _ in range(40)]
+    msgs = [b"pattern %d" % i for i in range(len(ks))]
+
+    def digits(k):
+        a = [(k // z**i) % z for i in range(4)]
+        return b"".join(a[i].to_bytes(8, "big") for i in (3, 2, 1, 0))
+
+    pts = _swu_points(b"".join(O.expand_message_xmd(m, O.DEFAULT_DST, 256) for m in msgs))
+    sig = (ctypes.c_uint8 * (96 * len(ks)))()
+    emu.lib().emu_sign_tail(bytes(pts), b"".join(digits(k) for k in ks), sig, ctypes.c_size_t(len(ks)))
+    want = C.sign_batch(b"".join(k.to_bytes(32, "big") for k in ks), msgs, O.DEFAULT_DST)
+    assert bytes(sig) == want
+
+
 def test_kernel_multiply_counts_used_by_the_bench():
     """bench.py's issued-multiply figures of the hand-written kernels are the counters of the host build of their source."""
     import ctypes
