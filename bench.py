@@ -555,7 +555,7 @@ def main():
                 "frac_sustained": per_gpu * IMAD_PER_PAIRING / imad_sustained,
                 "issued_per_pairing": {"imad_wide": IMAD_ISSUED_PER_PAIRING, "products": n_products, "reductions": n_reductions},
                 "issued": per_gpu * IMAD_ISSUED_PER_PAIRING / 1e12, "issued_frac_sustained": per_gpu * IMAD_ISSUED_PER_PAIRING / imad_sustained,
-                "traffic": 3841792, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE vm_kernel launch over 9472 pairings (ncu --set full): the 2.7 MB algorithmic bytes plus the program image; results are still in L2 when the kernel ends.  The kernel is compute-bound: the HBM fraction is ~1e-4",
+                "traffic": 4776448, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE vm_kernel launch over 9472 pairings (ncu --set full, profiles/r2_final2_ncu_pairing_sign.txt): the 2.7 MB algorithmic bytes plus the program image; results are still in L2 when the kernel ends.  The kernel is compute-bound: the HBM fraction is ~1e-4",
                 "note": "integer-multiply pipe bound (SURVEY 8d): achieved = pairings/s/GPU x 15.4k Fp-mul x 288 IMAD; peak = IMAD.WIDE.U32 issue rate measured live on this GPU in a 3 ms burst (bls381_imad_peak, boost clock); peak_sustained = the same microbenchmark back to back for 1 s (power-settled clock, the fair denominator for a step this long); issued = the multiply-adds the kernel actually executes (lazy-reduction program: more products, fewer reductions)",
                 "hbm": {"achieved": per_gpu * BYTES_PER_PAIRING / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * BYTES_PER_PAIRING / 1e9 / hbm_peak,
